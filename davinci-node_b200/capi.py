@@ -1,0 +1,65 @@
+"""ctypes binding of libb200groth16.so - the same symbols the Go shim binds with cgo
+(davinci-node_b200/go/prover_b200.go).  Every call raises B200Error on a non-zero status; nothing
+here computes on the CPU."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200groth16.so")
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(
+            "libb200groth16.so is missing (%s): build it with `python davinci-node_b200/build.py` - "
+            "this backend has no CPU fallback" % LIB_PATH)
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_vp, _u64, _u32, _i = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+
+_PROTOS = {
+    "b200_init": (_i, [_u32]),
+    "b200_device_count": (_i, []),
+    "b200_last_error": (C.c_char_p, []),
+    "b200_version": (C.c_char_p, []),
+    "b200_fr_bytes": (_u64, [_i]),
+    "b200_fp_bytes": (_u64, [_i]),
+    "b200_affine_bytes": (_u64, [_i, _i]),
+    "b200_xyzz_bytes": (_u64, [_i, _i]),
+    "b200_msm": (_i, [_i, _i, _vp, _vp, _u64, _vp, _i]),
+    "b200_msm_dev": (_i, [_i, _i, _vp, _vp, _u64, _vp, _i, _vp]),
+    "b200_to_affine_dev": (_i, [_i, _i, _vp, _vp, _u32, _vp]),
+    "b200_msm_plan": (_i, [_i, _u64, _i, C.POINTER(_u32)]),
+    "b200_dbg_field_op_dev": (_i, [_i, _i, _i, _vp, _vp, _vp, _u64, _vp]),
+    "b200_dbg_ec_op_dev": (_i, [_i, _i, _i, _vp, _vp, _vp, _u64, _vp]),
+    "b200_calib_mul_dev": (_i, [_i, _i, _vp, _u64, _i, _vp]),
+}
+
+EXPORTS = sorted(_PROTOS)
+
+for _name, (_res, _args) in _PROTOS.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(status):
+    if status != 0:
+        raise B200Error(lib.b200_last_error().decode("utf-8", "replace"))
+
+
+def init(device_mask=0):
+    check(lib.b200_init(device_mask))
+
+
+def msm_plan(curve, n, window_bits=0):
+    out = (_u32 * 5)()
+    check(lib.b200_msm_plan(curve, n, window_bits, out))
+    return dict(c=out[0], nwin=out[1], nb=out[2], task=out[3], group=out[4])

@@ -1,0 +1,108 @@
+// Host-side internal interface between the C-ABI (capi.cu) and the per-curve template
+// instantiations (curve_*.cu).  Not part of the public boundary (that is include/b200_groth16.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace b200 {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define B200_CUDA(expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      throw ::b200::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                              std::to_string(__LINE__) + ")");                                       \
+  } while (0)
+
+// Growable device scratch buffer (stream-ordered use; never shrinks).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t bytes) {
+    if (bytes > cap) {
+      if (p) B200_CUDA(cudaFree(p));
+      p = nullptr;
+      cap = 0;
+      size_t want = bytes + (bytes >> 3) + 256;
+      B200_CUDA(cudaMalloc(&p, want));
+      cap = want;
+    }
+    return p;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// Scratch for one MSM in flight (one per stream).
+struct MsmWorkspace {
+  DevBuf hist, off, cur, sorted, buckets, tasks, obuckets, partial, groups, windows, ctr;
+};
+
+struct MsmStats {
+  int c, nwin;
+  uint32_t nb, task, group;
+};
+
+enum FieldSel { FIELD_FP = 0, FIELD_FR = 1, FIELD_FP2 = 2 };
+enum FieldOp { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_SQR = 3, OP_FROM_MONT = 4, OP_TO_MONT = 5, OP_INV = 6, OP_NEG = 7 };
+enum EcOp { EC_MADD = 0, EC_ADD = 1, EC_DBL = 2, EC_TO_AFFINE = 3, EC_MUL_SCALAR = 4 };
+
+struct NttWorkspace;
+
+// One implementation per curve (template instantiation in curve_<name>.cu).
+struct CurveBackend {
+  virtual ~CurveBackend() = default;
+  virtual int id() const = 0;
+  virtual const char* name() const = 0;
+  virtual size_t fr_bytes() const = 0;
+  virtual size_t fp_bytes() const = 0;
+  virtual size_t affine_bytes(int group) const = 0;   // group: 1 = G1, 2 = G2
+  virtual size_t xyzz_bytes(int group) const = 0;
+  virtual int fr_bits() const = 0;
+
+  // --- MSM: device pointers, result (one XYZZ point) written to d_out; fully asynchronous on `s`
+  virtual void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out_xyzz,
+                   MsmWorkspace& ws, cudaStream_t s, int c_override, MsmStats* stats) = 0;
+  // --- point helpers
+  virtual void to_affine(int group, const void* d_xyzz, void* d_affine, uint32_t count, cudaStream_t s) = 0;
+  // out = sum_i [k_i] P_i  (tiny, single thread): used for the alpha/beta/delta terms of the proof
+  // --- debug / parity entry points (element-wise, device pointers)
+  virtual void dbg_field_op(int field, int op, const void* a, const void* b, void* out, uint64_t n,
+                            cudaStream_t s) = 0;
+  virtual void dbg_ec_op(int group, int op, const void* a, const void* b, void* out, uint64_t n,
+                         cudaStream_t s) = 0;
+  // --- throughput calibration: `iters` dependent Montgomery multiplications per thread (fp)
+  virtual void calib_mul(int field, void* d_inout, uint64_t nthreads, int iters, cudaStream_t s) = 0;
+};
+
+CurveBackend* backend_bn254();
+CurveBackend* backend_bls12_377();
+CurveBackend* backend_bls12_381();
+CurveBackend* backend_bw6_761();
+
+inline CurveBackend* backend_by_id(int id) {
+  switch (id) {
+    case 1: return backend_bn254();
+    case 2: return backend_bls12_377();
+    case 3: return backend_bls12_381();
+    case 4: return backend_bw6_761();
+    default: return nullptr;
+  }
+}
+
+}  // namespace b200

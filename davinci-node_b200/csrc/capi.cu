@@ -1,0 +1,198 @@
+// C ABI of libb200groth16.so (see include/b200_groth16.h for the contract and the reference
+// interfaces each symbol replaces).  Host-side glue only: argument checking, device selection,
+// workspace pooling, error capture.  No arithmetic happens on the CPU.
+#include "../../include/b200_groth16.h"
+
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+
+#include "backend.h"
+#include "msm_plan.h"
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+
+template <class Fn>
+int guarded(Fn fn) {
+  try {
+    fn();
+    return 0;
+  } catch (const std::exception& e) {
+    return fail(e.what());
+  } catch (...) {
+    return fail("unknown error");
+  }
+}
+
+std::mutex g_mu;
+uint32_t g_mask = 0;
+bool g_inited = false;
+
+// one workspace per (device, stream); guarded by g_mu for lookup only
+std::map<std::pair<int, void*>, std::unique_ptr<MsmWorkspace>> g_ws;
+
+MsmWorkspace& workspace_for(int dev, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto& slot = g_ws[{dev, stream}];
+  if (!slot) slot.reset(new MsmWorkspace());
+  return *slot;
+}
+
+CurveBackend& curve(int id) {
+  CurveBackend* b = backend_by_id(id);
+  if (!b) throw std::runtime_error("unsupported curve id " + std::to_string(id));
+  return *b;
+}
+
+void check_group(int g) {
+  if (g != 1 && g != 2) throw std::runtime_error("group must be 1 (G1) or 2 (G2)");
+}
+
+int current_device() {
+  int d = 0;
+  B200_CUDA(cudaGetDevice(&d));
+  return d;
+}
+
+struct DeviceGuard {
+  int prev;
+  explicit DeviceGuard(int dev) {
+    B200_CUDA(cudaGetDevice(&prev));
+    if (dev != prev) B200_CUDA(cudaSetDevice(dev));
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+struct ScopedStream {
+  cudaStream_t s = nullptr;
+  ScopedStream() { B200_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+  ~ScopedStream() {
+    if (s) cudaStreamDestroy(s);
+  }
+};
+
+struct ScopedDev {
+  void* p = nullptr;
+  explicit ScopedDev(size_t bytes) { B200_CUDA(cudaMalloc(&p, bytes ? bytes : 16)); }
+  ~ScopedDev() {
+    if (p) cudaFree(p);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+const char* b200_version(void) { return "b200-groth16 0.1 (sm_100a)"; }
+
+int b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int b200_init(uint32_t device_mask) {
+  return guarded([&] {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int n = 0;
+    B200_CUDA(cudaGetDeviceCount(&n));
+    if (n == 0) throw std::runtime_error("no CUDA device visible (this backend has no CPU fallback)");
+    for (int d = 0; d < n; d++) {
+      cudaDeviceProp p;
+      B200_CUDA(cudaGetDeviceProperties(&p, d));
+      if (p.major != 10)
+        throw std::runtime_error("device " + std::to_string(d) + " is sm_" + std::to_string(p.major * 10 + p.minor) +
+                                 "; this library contains sm_100a code only");
+    }
+    g_mask = device_mask ? device_mask : ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u));
+    g_inited = true;
+  });
+}
+
+uint64_t b200_fr_bytes(int c) { return backend_by_id(c) ? backend_by_id(c)->fr_bytes() : 0; }
+uint64_t b200_fp_bytes(int c) { return backend_by_id(c) ? backend_by_id(c)->fp_bytes() : 0; }
+uint64_t b200_affine_bytes(int c, int g) { return backend_by_id(c) ? backend_by_id(c)->affine_bytes(g) : 0; }
+uint64_t b200_xyzz_bytes(int c, int g) { return backend_by_id(c) ? backend_by_id(c)->xyzz_bytes(g) : 0; }
+
+int b200_msm_dev(int curve_id, int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out,
+                 int window_bits, void* stream) {
+  return guarded([&] {
+    check_group(group);
+    if (window_bits < 0 || window_bits > 24) throw std::runtime_error("window_bits out of range");
+    CurveBackend& cb = curve(curve_id);
+    MsmWorkspace& ws = workspace_for(current_device(), stream);
+    cb.msm(group, d_points, d_scalars, n, d_out, ws, (cudaStream_t)stream, window_bits, nullptr);
+  });
+}
+
+int b200_msm_plan(int curve_id, uint64_t n, int window_bits, uint32_t out[5]) {
+  return guarded([&] {
+    CurveBackend& cb = curve(curve_id);
+    MsmPlan st = make_msm_plan(n, cb.fr_bits(), window_bits);
+    out[0] = st.c;
+    out[1] = st.nwin;
+    out[2] = st.nb;
+    out[3] = st.task;
+    out[4] = st.group;
+  });
+}
+
+int b200_to_affine_dev(int curve_id, int group, const void* d_xyzz, void* d_affine, uint32_t count, void* stream) {
+  return guarded([&] {
+    check_group(group);
+    curve(curve_id).to_affine(group, d_xyzz, d_affine, count, (cudaStream_t)stream);
+  });
+}
+
+int b200_msm(int curve_id, int group, const void* points, const void* scalars, uint64_t n, void* out_affine,
+             int device) {
+  return guarded([&] {
+    check_group(group);
+    CurveBackend& cb = curve(curve_id);
+    if (!out_affine) throw std::runtime_error("out_affine is null");
+    if (n && (!points || !scalars)) throw std::runtime_error("null input with n > 0");
+    DeviceGuard dg(device);
+    ScopedStream st;
+    const size_t pb = cb.affine_bytes(group), sb = cb.fr_bytes();
+    ScopedDev dp(n * pb), dsc(n * sb), dout(cb.xyzz_bytes(group)), daff(pb);
+    if (n) {
+      B200_CUDA(cudaMemcpyAsync(dp.p, points, n * pb, cudaMemcpyHostToDevice, st.s));
+      B200_CUDA(cudaMemcpyAsync(dsc.p, scalars, n * sb, cudaMemcpyHostToDevice, st.s));
+    }
+    MsmWorkspace ws;
+    cb.msm(group, dp.p, dsc.p, n, dout.p, ws, st.s, 0, nullptr);
+    cb.to_affine(group, dout.p, daff.p, 1, st.s);
+    B200_CUDA(cudaMemcpyAsync(out_affine, daff.p, pb, cudaMemcpyDeviceToHost, st.s));
+    B200_CUDA(cudaStreamSynchronize(st.s));
+  });
+}
+
+int b200_dbg_field_op_dev(int curve_id, int field, int op, const void* a, const void* b, void* out, uint64_t n,
+                          void* stream) {
+  return guarded([&] { curve(curve_id).dbg_field_op(field, op, a, b, out, n, (cudaStream_t)stream); });
+}
+
+int b200_dbg_ec_op_dev(int curve_id, int group, int op, const void* a, const void* b, void* out, uint64_t n,
+                       void* stream) {
+  return guarded([&] {
+    check_group(group);
+    curve(curve_id).dbg_ec_op(group, op, a, b, out, n, (cudaStream_t)stream);
+  });
+}
+
+int b200_calib_mul_dev(int curve_id, int field, void* d_inout, uint64_t nthreads, int iters, void* stream) {
+  return guarded([&] { curve(curve_id).calib_mul(field, d_inout, nthreads, iters, (cudaStream_t)stream); });
+}
+
+}  // extern "C"

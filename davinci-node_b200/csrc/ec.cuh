@@ -1,0 +1,244 @@
+// Elliptic-curve group law for y^2 = x^3 + b (a = 0 on every curve of the path), templated on the
+// coordinate field F (FpT<...> for G1 and BW6-761 G2, Fp2T<...> for the other G2 groups).
+//
+// Buckets and partial sums live in extended-Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ,
+// ZZ^3 = ZZZ^2): mixed addition costs 8M+2S, the cheapest inversion-free bucket update.
+// Affine points use gnark-crypto's layout {X, Y}, infinity = (0, 0)  (SURVEY.md A.4).
+//
+// Replaces gnark-crypto's g1JacExtended / g2JacExtended bucket arithmetic used by
+// `G1Affine.MultiExp` / `G2Affine.MultiExp` under groth16.Prove
+// (/root/reference/prover/prover_cpu.go:37).
+#pragma once
+#include "field.cuh"
+
+namespace b200 {
+
+template <class F>
+struct alignas(16) Affine {
+  typename F::El x, y;
+};
+
+template <class F>
+struct alignas(16) XYZZ {
+  typename F::El x, y, zz, zzz;
+};
+
+template <class F>
+struct EC {
+  using El = typename F::El;
+  using Aff = Affine<F>;
+  using Pt = XYZZ<F>;
+
+  static __device__ __forceinline__ void set_inf(Pt& p) {
+    F::set_zero(p.x);
+    F::set_zero(p.y);
+    F::set_zero(p.zz);
+    F::set_zero(p.zzz);
+  }
+  static __device__ __forceinline__ bool is_inf(const Pt& p) { return F::is_zero(p.zz); }
+  static __device__ __forceinline__ bool is_inf(const Aff& p) { return F::is_zero(p.x) && F::is_zero(p.y); }
+  static __device__ __forceinline__ void from_affine(Pt& r, const Aff& p) {
+    if (is_inf(p)) {
+      set_inf(r);
+      return;
+    }
+    r.x = p.x;
+    r.y = p.y;
+    F::set_one(r.zz);
+    F::set_one(r.zzz);
+  }
+  static __device__ __forceinline__ void neg(Aff& p) { F::neg(p.y, p.y); }
+  static __device__ __forceinline__ void neg(Pt& p) { F::neg(p.y, p.y); }
+
+  // r = 2 * (affine p)          (mdbl-2008-s-1)
+  static __device__ __noinline__ void dbl_affine(Pt& r, const Aff& p) {
+    El u, v, w, s, m, t;
+    F::dbl(u, p.y);
+    F::sqr(v, u);
+    F::mul(w, u, v);
+    F::mul(s, p.x, v);
+    F::sqr(m, p.x);
+    F::dbl(t, m);
+    F::add(m, m, t);          // 3 x^2
+    F::sqr(r.x, m);
+    F::sub(r.x, r.x, s);
+    F::sub(r.x, r.x, s);
+    F::sub(t, s, r.x);
+    F::mul(t, m, t);
+    F::mul(u, w, p.y);
+    F::sub(r.y, t, u);
+    r.zz = v;
+    r.zzz = w;
+  }
+
+  // p = 2 * p                   (dbl-2008-s-1)
+  static __device__ __noinline__ void dbl(Pt& p) {
+    if (is_inf(p)) return;
+    El u, v, w, s, m, t;
+    F::dbl(u, p.y);
+    F::sqr(v, u);
+    F::mul(w, u, v);
+    F::mul(s, p.x, v);
+    F::sqr(m, p.x);
+    F::dbl(t, m);
+    F::add(m, m, t);
+    F::mul(u, w, p.y);        // W * Y1 (before Y is overwritten)
+    F::sqr(p.x, m);
+    F::sub(p.x, p.x, s);
+    F::sub(p.x, p.x, s);
+    F::sub(t, s, p.x);
+    F::mul(t, m, t);
+    F::sub(p.y, t, u);
+    F::mul(p.zz, v, p.zz);
+    F::mul(p.zzz, w, p.zzz);
+  }
+
+  // acc += (affine p)           (madd-2008-s), all special cases handled
+  static __device__ __forceinline__ void madd(Pt& acc, const Aff& p) {
+    if (is_inf(p)) return;
+    if (is_inf(acc)) {
+      acc.x = p.x;
+      acc.y = p.y;
+      F::set_one(acc.zz);
+      F::set_one(acc.zzz);
+      return;
+    }
+    El u2, s2, pp, ppp, q, t;
+    F::mul(u2, p.x, acc.zz);
+    F::mul(s2, p.y, acc.zzz);
+    F::sub(u2, u2, acc.x);     // P
+    F::sub(s2, s2, acc.y);     // R
+    if (F::is_zero(u2)) {
+      if (F::is_zero(s2)) {
+        dbl_affine(acc, p);
+      } else {
+        set_inf(acc);
+      }
+      return;
+    }
+    F::sqr(pp, u2);
+    F::mul(ppp, u2, pp);
+    F::mul(q, acc.x, pp);
+    F::sqr(t, s2);
+    F::sub(t, t, ppp);
+    F::sub(t, t, q);
+    F::sub(acc.x, t, q);       // X3 = R^2 - PPP - 2Q
+    F::sub(q, q, acc.x);
+    F::mul(q, s2, q);          // R (Q - X3)
+    F::mul(t, acc.y, ppp);
+    F::sub(acc.y, q, t);
+    F::mul(acc.zz, acc.zz, pp);
+    F::mul(acc.zzz, acc.zzz, ppp);
+  }
+
+  // acc += b                    (add-2008-s), all special cases handled
+  static __device__ __noinline__ void add(Pt& acc, const Pt& b) {
+    if (is_inf(b)) return;
+    if (is_inf(acc)) {
+      acc = b;
+      return;
+    }
+    El u1, u2, s1, s2, pp, ppp, q, t;
+    F::mul(u1, acc.x, b.zz);
+    F::mul(u2, b.x, acc.zz);
+    F::mul(s1, acc.y, b.zzz);
+    F::mul(s2, b.y, acc.zzz);
+    F::sub(u2, u2, u1);        // P
+    F::sub(s2, s2, s1);        // R
+    if (F::is_zero(u2)) {
+      if (F::is_zero(s2)) {
+        dbl(acc);
+      } else {
+        set_inf(acc);
+      }
+      return;
+    }
+    F::sqr(pp, u2);
+    F::mul(ppp, u2, pp);
+    F::mul(q, u1, pp);
+    F::sqr(t, s2);
+    F::sub(t, t, ppp);
+    F::sub(t, t, q);
+    F::sub(acc.x, t, q);
+    F::sub(q, q, acc.x);
+    F::mul(q, s2, q);
+    F::mul(t, s1, ppp);
+    F::sub(acc.y, q, t);
+    F::mul(acc.zz, acc.zz, b.zz);
+    F::mul(acc.zz, acc.zz, pp);
+    F::mul(acc.zzz, acc.zzz, b.zzz);
+    F::mul(acc.zzz, acc.zzz, ppp);
+  }
+
+  // r = [k] p for a small unsigned k (double-and-add, MSB first)
+  static __device__ __noinline__ void mul_u32(Pt& r, const Pt& p, uint32_t k) {
+    Pt acc;
+    set_inf(acc);
+    for (int i = 31; i >= 0; i--) {
+      dbl(acc);
+      if ((k >> i) & 1) add(acc, p);
+    }
+    r = acc;
+  }
+
+  // r = [s] p for a canonical (non-Montgomery) little-endian scalar of NS limbs
+  template <int NS>
+  static __device__ __noinline__ void mul_scalar(Pt& r, const Pt& p, const uint32_t* s) {
+    Pt acc;
+    set_inf(acc);
+    bool started = false;
+    for (int i = NS * 32 - 1; i >= 0; i--) {
+      if (started) dbl(acc);
+      if ((s[i >> 5] >> (i & 31)) & 1) {
+        add(acc, p);
+        started = true;
+      }
+    }
+    r = acc;
+  }
+
+  // affine normalisation: x = X/ZZ, y = Y/ZZZ ; infinity -> (0, 0)
+  static __device__ __noinline__ void to_affine(Aff& r, const Pt& p) {
+    if (is_inf(p)) {
+      F::set_zero(r.x);
+      F::set_zero(r.y);
+      return;
+    }
+    // 1/ZZ and 1/ZZZ from a single inversion of ZZ*ZZZ
+    El t, ti;
+    F::mul(t, p.zz, p.zzz);
+    F::inv(ti, t);
+    El izz, izzz;
+    F::mul(izz, ti, p.zzz);
+    F::mul(izzz, ti, p.zz);
+    F::mul(r.x, p.x, izz);
+    F::mul(r.y, p.y, izzz);
+  }
+};
+
+// 128-bit vectorised global load / store of POD structs whose size is a multiple of 16 bytes
+template <class T>
+__device__ __forceinline__ void load16(T& dst, const T* src) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte multiple expected");
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(&dst);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldg(s + i);
+}
+template <class T>
+__device__ __forceinline__ void load16_rw(T& dst, const T* src) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(&dst);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+template <class T>
+__device__ __forceinline__ void store16(T* dst, const T& src) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte multiple expected");
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint4* s = reinterpret_cast<const uint4*>(&src);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+
+}  // namespace b200

@@ -1,0 +1,216 @@
+// Field layer for the sm_100a Groth16 backend.
+//
+// The limb-level arithmetic is generated (tools/gen_field.py -> gen/field_*.cuh): one inline-PTX
+// block per operation, IMAD.WIDE carry chains, modulus as immediates.  This header wraps a generated
+// parameter struct P into the "field concept" the EC / MSM / NTT templates consume:
+//
+//   F::El                      element type (plain limbs, gnark-crypto Montgomery layout)
+//   F::add/sub/mul/sqr/dbl/neg (El& r, const El& a[, const El& b])     r may alias a/b
+//   F::is_zero / eq / set_zero / set_one
+//   F::LIMBS                   uint32 words per element
+//
+// Replaces gnark-crypto `fp.Element` / `fr.Element` / `E2` arithmetic reached from
+// /root/reference/prover/prover_cpu.go:37 (groth16.Prove).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#include "gen/field_bn254_fp.cuh"
+#include "gen/field_bn254_fr.cuh"
+#include "gen/field_bls12_377_fp.cuh"
+#include "gen/field_bls12_377_fr.cuh"
+#include "gen/field_bls12_381_fp.cuh"
+#include "gen/field_bls12_381_fr.cuh"
+#include "gen/field_bw6_761_fp.cuh"
+
+namespace b200 {
+
+using bw6_761_fr = bls12_377_fp;   // BW6-761's scalar field is BLS12-377's base field (2-chain)
+
+template <int N>
+struct alignas(16) Limbs {
+  uint32_t v[N];
+};
+
+// ---------------------------------------------------------------------------------------- Fp
+template <class P>
+struct FpT {
+  using Params = P;
+  static constexpr int N = P::N;
+  static constexpr int LIMBS = P::N;
+  static constexpr int BITS = P::BITS;
+  using El = Limbs<N>;
+
+  static __device__ __forceinline__ void add(El& r, const El& a, const El& b) { P::add(r.v, a.v, b.v); }
+  static __device__ __forceinline__ void sub(El& r, const El& a, const El& b) { P::sub(r.v, a.v, b.v); }
+  static __device__ __forceinline__ void mul(El& r, const El& a, const El& b) { P::mul(r.v, a.v, b.v); }
+  static __device__ __forceinline__ void sqr(El& r, const El& a) { P::sqr(r.v, a.v); }
+  static __device__ __forceinline__ void dbl(El& r, const El& a) { P::add(r.v, a.v, a.v); }
+  static __device__ __forceinline__ void from_mont(El& r, const El& a) { P::from_mont(r.v, a.v); }
+  static __device__ __forceinline__ void to_mont(El& r, const El& a) {
+    El r2;
+#pragma unroll
+    for (int i = 0; i < N; i++) r2.v[i] = P::r2(i);
+    P::mul(r.v, a.v, r2.v);
+  }
+  static __device__ __forceinline__ void set_zero(El& r) {
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = 0;
+  }
+  static __device__ __forceinline__ void set_one(El& r) {
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+  }
+  static __device__ __forceinline__ bool is_zero(const El& a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= a.v[i];
+    return o == 0;
+  }
+  static __device__ __forceinline__ bool eq(const El& a, const El& b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= a.v[i] ^ b.v[i];
+    return o == 0;
+  }
+  static __device__ __forceinline__ void neg(El& r, const El& a) {
+    El z;
+    set_zero(z);
+    P::sub(r.v, z.v, a.v);   // 0 - a mod p  (gives 0 for a == 0)
+  }
+  // r = a * k for a small non-negative compile-time-ish integer (used for curve constants 3, 5 ...)
+  static __device__ __forceinline__ void mul_small(El& r, const El& a, int k) {
+    El acc, base = a;
+    set_zero(acc);
+    while (k) {
+      if (k & 1) add(acc, acc, base);
+      k >>= 1;
+      if (k) dbl(base, base);
+    }
+    r = acc;
+  }
+  // a^e for a canonical little-endian exponent of NE limbs (square-and-multiply, MSB first)
+  template <int NE>
+  static __device__ __noinline__ void pow(El& r, const El& a, const uint32_t* e) {
+    El acc;
+    set_one(acc);
+    bool started = false;
+    for (int i = NE * 32 - 1; i >= 0; i--) {
+      if (started) sqr(acc, acc);
+      if ((e[i >> 5] >> (i & 31)) & 1) {
+        mul(acc, acc, a);
+        started = true;
+      }
+    }
+    r = acc;
+  }
+  // a^-1 = a^(p-2); 0 -> 0
+  static __device__ __noinline__ void inv(El& r, const El& a) {
+    uint32_t e[N];
+    uint32_t borrow = 2;   // e = p - 2 (low limb is 1 for the BLS12-377 fields and BLS12-381 fr)
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      uint32_t m = P::modulus(i);
+      e[i] = m - borrow;
+      borrow = (m < borrow) ? 1u : 0u;
+    }
+    pow<N>(r, a, e);
+  }
+};
+
+// ---------------------------------------------------------------------------------------- Fp2
+// Fp2 = Fp[u] / (u^2 + NR_NEG)   i.e. u^2 = -NR_NEG   (1 for BN254 / BLS12-381, 5 for BLS12-377)
+template <class P, int NR_NEG>
+struct Fp2T {
+  using Base = FpT<P>;
+  using BEl = typename Base::El;
+  static constexpr int LIMBS = 2 * P::N;
+  struct alignas(16) El {
+    BEl c0, c1;
+  };
+
+  static __device__ __forceinline__ void add(El& r, const El& a, const El& b) {
+    Base::add(r.c0, a.c0, b.c0);
+    Base::add(r.c1, a.c1, b.c1);
+  }
+  static __device__ __forceinline__ void sub(El& r, const El& a, const El& b) {
+    Base::sub(r.c0, a.c0, b.c0);
+    Base::sub(r.c1, a.c1, b.c1);
+  }
+  static __device__ __forceinline__ void dbl(El& r, const El& a) {
+    Base::dbl(r.c0, a.c0);
+    Base::dbl(r.c1, a.c1);
+  }
+  static __device__ __forceinline__ void neg(El& r, const El& a) {
+    Base::neg(r.c0, a.c0);
+    Base::neg(r.c1, a.c1);
+  }
+  static __device__ __forceinline__ void mul_nr_neg(BEl& r, const BEl& a) {   // r = NR_NEG * a
+    if (NR_NEG == 1) {
+      r = a;
+    } else {   // 5a = 4a + a
+      BEl t;
+      Base::dbl(t, a);
+      Base::dbl(t, t);
+      Base::add(r, t, a);
+    }
+  }
+  // Karatsuba: 3 base multiplications
+  static __device__ __noinline__ void mul(El& r, const El& a, const El& b) {
+    BEl t0, t1, sa, sb;
+    Base::mul(t0, a.c0, b.c0);
+    Base::mul(t1, a.c1, b.c1);
+    Base::add(sa, a.c0, a.c1);
+    Base::add(sb, b.c0, b.c1);
+    Base::mul(sa, sa, sb);
+    Base::sub(sa, sa, t0);
+    Base::sub(r.c1, sa, t1);
+    mul_nr_neg(t1, t1);
+    Base::sub(r.c0, t0, t1);
+  }
+  static __device__ __noinline__ void sqr(El& r, const El& a) {
+    // c1 = 2 a0 a1 ; c0 = a0^2 - NR_NEG a1^2 = (a0 + a1)(a0 - NR_NEG a1) + (NR_NEG - 1) a0 a1
+    BEl m, s, d, t;
+    Base::mul(m, a.c0, a.c1);
+    Base::add(s, a.c0, a.c1);
+    mul_nr_neg(t, a.c1);
+    Base::sub(d, a.c0, t);
+    Base::mul(s, s, d);
+    if (NR_NEG == 1) {
+      r.c0 = s;
+    } else {
+      Base::dbl(t, m);
+      Base::dbl(t, t);   // 4 a0 a1
+      Base::add(r.c0, s, t);
+    }
+    Base::dbl(r.c1, m);
+  }
+  static __device__ __forceinline__ void set_zero(El& r) {
+    Base::set_zero(r.c0);
+    Base::set_zero(r.c1);
+  }
+  static __device__ __forceinline__ void set_one(El& r) {
+    Base::set_one(r.c0);
+    Base::set_zero(r.c1);
+  }
+  static __device__ __forceinline__ bool is_zero(const El& a) { return Base::is_zero(a.c0) && Base::is_zero(a.c1); }
+  static __device__ __forceinline__ bool eq(const El& a, const El& b) { return Base::eq(a.c0, b.c0) && Base::eq(a.c1, b.c1); }
+  static __device__ __forceinline__ void mul_small(El& r, const El& a, int k) {
+    Base::mul_small(r.c0, a.c0, k);
+    Base::mul_small(r.c1, a.c1, k);
+  }
+  static __device__ __noinline__ void inv(El& r, const El& a) {
+    // 1/(a0 + a1 u) = (a0 - a1 u) / (a0^2 + NR_NEG a1^2)
+    BEl n, t;
+    Base::sqr(n, a.c0);
+    Base::sqr(t, a.c1);
+    mul_nr_neg(t, t);
+    Base::add(n, n, t);
+    Base::inv(n, n);
+    Base::mul(r.c0, a.c0, n);
+    Base::mul(t, a.c1, n);
+    Base::neg(r.c1, t);
+  }
+};
+
+}  // namespace b200

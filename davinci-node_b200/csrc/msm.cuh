@@ -1,0 +1,321 @@
+// Signed-digit Pippenger multi-scalar multiplication for sm_100a.
+//
+//   digits/histogram -> per-window exclusive scan -> counting-sort scatter (point index | sign)
+//   -> bucket accumulation (one thread per bucket, 128-bit gathered affine loads, XYZZ mixed adds;
+//      oversized buckets are split into fixed-size tasks and merged by a block reduction)
+//   -> bucket reduction (running sums over groups of buckets, [base]*sum fix-up per group)
+//   -> per-window block reduction -> Horner combine of the windows.
+//
+// Everything runs on one stream with no host synchronisation; scalars are consumed in
+// gnark-crypto's Montgomery form (converted in-register), points in gnark's affine layout.
+//
+// Replaces `G1Affine.MultiExp` / `G2Affine.MultiExp` (gnark-crypto, go.mod:16) as called for the
+// Ar / Bs1 / Bs / Krs / Krs2 and Pedersen commitments of groth16.Prove
+// (/root/reference/prover/prover_cpu.go:37).
+#pragma once
+#include "ec.cuh"
+#include "msm_plan.h"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------ digits
+// canonical scalar -> signed digit of window w (c <= 30).  `s` has NS limbs.
+template <int NS>
+__device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int bit, int c) {
+  int limb = bit >> 5, off = bit & 31;
+  if (limb >= NS) return 0;
+  uint64_t two = s[limb];
+  if (limb + 1 < NS) two |= (uint64_t)s[limb + 1] << 32;
+  return (uint32_t)(two >> off) & ((1u << c) - 1u);
+}
+
+// Walk all windows of one scalar, calling f(w, bucket_index (0-based), negative)
+template <class Fr, class Fn>
+__device__ __forceinline__ void for_each_digit(const typename Fr::El& mont, const MsmPlan& pl, Fn f) {
+  typename Fr::El s;
+  Fr::from_mont(s, mont);
+  if (Fr::is_zero(s)) return;
+  uint32_t carry = 0;
+  const uint32_t half = 1u << (pl.c - 1);
+  for (int w = 0; w < pl.nwin; w++) {
+    uint32_t d = window_bits<Fr::N>(s.v, w * pl.c, pl.c) + carry;
+    carry = 0;
+    bool neg = false;
+    if (d > half) {
+      d = (1u << pl.c) - d;
+      neg = true;
+      carry = 1;
+    }
+    if (d) f(w, d - 1, neg);
+  }
+}
+
+template <class Fr>
+__global__ void k_msm_hist(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ hist) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pl.n) return;
+  typename Fr::El s;
+  load16(s, scalars + i);
+  for_each_digit<Fr>(s, pl, [&](int w, uint32_t b, bool) { atomicAdd(&hist[(uint64_t)w * pl.nb + b], 1u); });
+}
+
+// one block per window: exclusive scan of hist -> off (start offsets) and cur (running cursors)
+static __global__ void k_msm_scan(const uint32_t* __restrict__ hist, MsmPlan pl, uint32_t* __restrict__ off,
+                           uint32_t* __restrict__ cur) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  const uint32_t* h = hist + (uint64_t)blockIdx.x * pl.nb;
+  uint32_t* o = off + (uint64_t)blockIdx.x * pl.nb;
+  uint32_t* c = cur + (uint64_t)blockIdx.x * pl.nb;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (uint32_t base = 0; base < pl.nb; base += blockDim.x) {
+    uint32_t idx = base + threadIdx.x;
+    uint32_t v = idx < pl.nb ? h[idx] : 0;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t ws = lane < nw ? warp_sums[lane] : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, ws, d);
+        if (lane >= d) ws += y;
+      }
+      warp_sums[lane] = ws;   // inclusive
+    }
+    __syncthreads();
+    uint32_t prefix = carry_s + (wid ? warp_sums[wid - 1] : 0) + (x - v);
+    if (idx < pl.nb) {
+      o[idx] = prefix;
+      c[idx] = prefix;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = prefix + v;
+    __syncthreads();
+  }
+}
+
+template <class Fr>
+__global__ void k_msm_scatter(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ cur,
+                              uint32_t* __restrict__ sorted) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pl.n) return;
+  typename Fr::El s;
+  load16(s, scalars + i);
+  for_each_digit<Fr>(s, pl, [&](int w, uint32_t b, bool neg) {
+    uint32_t pos = atomicAdd(&cur[(uint64_t)w * pl.nb + b], 1u);
+    sorted[(uint64_t)w * pl.n + pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
+  });
+}
+
+// ------------------------------------------------------------------------------------ accumulate
+struct OvfTask {
+  uint32_t bucket;   // global bucket id  w * nb + b
+  uint32_t start;    // offset inside the window's sorted segment
+  uint32_t len;
+  uint32_t pad;
+};
+struct OvfBucket {
+  uint32_t bucket;
+  uint32_t first;    // first task index
+  uint32_t ntasks;
+  uint32_t pad;
+};
+struct OvfCounters {
+  uint32_t ntasks;
+  uint32_t nbuckets;
+};
+
+template <class F>
+__device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const Affine<F>* __restrict__ points,
+                                               const uint32_t* __restrict__ idx, uint32_t len) {
+  using E = EC<F>;
+  E::set_inf(acc);
+  if (len == 0) return;
+  // software pipeline: the next point is in flight while the current mixed add runs
+  uint32_t e = idx[0];
+  Affine<F> nxt;
+  load16(nxt, points + (e & 0x7fffffffu));
+  for (uint32_t k = 0; k < len; k++) {
+    Affine<F> cur = nxt;
+    bool neg = e >> 31;
+    if (k + 1 < len) {
+      e = idx[k + 1];
+      load16(nxt, points + (e & 0x7fffffffu));
+    }
+    if (neg) E::neg(cur);
+    E::madd(acc, cur);
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted,
+                 const uint32_t* __restrict__ off, const uint32_t* __restrict__ end, MsmPlan pl,
+                 XYZZ<F>* __restrict__ buckets, OvfTask* __restrict__ tasks, OvfBucket* __restrict__ obuckets,
+                 OvfCounters* __restrict__ ctr) {
+  uint64_t gb = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gb >= (uint64_t)pl.nwin * pl.nb) return;
+  uint32_t w = (uint32_t)(gb / pl.nb);
+  uint32_t start = off[gb], cnt = end[gb] - start;
+  uint32_t mine = cnt;
+  if (cnt > pl.task) {
+    mine = pl.task;
+    uint32_t extra = (cnt - pl.task + pl.task - 1) / pl.task;
+    uint32_t first = atomicAdd(&ctr->ntasks, extra);
+    if (first + extra <= pl.max_ovf) {
+      uint32_t ob = atomicAdd(&ctr->nbuckets, 1u);
+      obuckets[ob] = OvfBucket{(uint32_t)gb, first, extra, 0};
+      uint32_t s = start + pl.task, left = cnt - pl.task;
+      for (uint32_t t = 0; t < extra; t++) {
+        uint32_t l = left < pl.task ? left : pl.task;
+        tasks[first + t] = OvfTask{(uint32_t)gb, s, l, 0};
+        s += l;
+        left -= l;
+      }
+    } else {
+      mine = cnt;   // cannot happen (capacity is n*nwin/task + nwin*nb); stay correct anyway
+    }
+  }
+  XYZZ<F> acc;
+  accumulate_run<F>(acc, points, sorted + (uint64_t)w * pl.n + start, mine);
+  store16(buckets + gb, acc);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128)
+k_msm_ovf_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted, MsmPlan pl,
+                     const OvfTask* __restrict__ tasks, const OvfCounters* __restrict__ ctr,
+                     XYZZ<F>* __restrict__ partial) {
+  uint32_t nt = ctr->ntasks < pl.max_ovf ? ctr->ntasks : pl.max_ovf;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    OvfTask tk = tasks[t];
+    uint32_t w = tk.bucket / pl.nb;
+    XYZZ<F> acc;
+    accumulate_run<F>(acc, points, sorted + (uint64_t)w * pl.n + tk.start, tk.len);
+    store16(partial + t, acc);
+  }
+}
+
+// Block-wide sum of XYZZ points through shared memory; result valid in thread 0.
+template <class F, int THREADS>
+__device__ __forceinline__ void block_sum(XYZZ<F>& v, XYZZ<F>* sm) {
+  using E = EC<F>;
+  store16(sm + threadIdx.x, v);
+  __syncthreads();
+  for (int s = THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      XYZZ<F> o;
+      load16_rw(o, sm + threadIdx.x + s);
+      E::add(v, o);
+      store16(sm + threadIdx.x, v);
+    }
+    __syncthreads();
+  }
+}
+
+constexpr int kReduceThreads = 64;
+
+// one block per oversized bucket: bucket += sum of its task partials
+template <class F>
+__global__ void __launch_bounds__(kReduceThreads)
+k_msm_ovf_merge(const OvfBucket* __restrict__ obuckets, const OvfCounters* __restrict__ ctr,
+                const XYZZ<F>* __restrict__ partial, XYZZ<F>* __restrict__ buckets) {
+  extern __shared__ uint4 smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  using E = EC<F>;
+  uint32_t nbk = ctr->nbuckets;
+  for (uint32_t ob = blockIdx.x; ob < nbk; ob += gridDim.x) {
+    OvfBucket b = obuckets[ob];
+    XYZZ<F> acc;
+    E::set_inf(acc);
+    for (uint32_t t = threadIdx.x; t < b.ntasks; t += kReduceThreads) {
+      XYZZ<F> p;
+      load16_rw(p, partial + b.first + t);
+      E::add(acc, p);
+    }
+    block_sum<F, kReduceThreads>(acc, sm);
+    if (threadIdx.x == 0) {
+      XYZZ<F> cur;
+      load16_rw(cur, buckets + b.bucket);
+      E::add(cur, acc);
+      store16(buckets + b.bucket, cur);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------ bucket reduction
+// thread (w, g): sum_{k in group g} (k+1) * B[w][k]  ->  groups[w * ngroups + g]
+template <class F>
+__global__ void __launch_bounds__(64)
+k_msm_bucket_reduce(const XYZZ<F>* __restrict__ buckets, MsmPlan pl, XYZZ<F>* __restrict__ groups) {
+  using E = EC<F>;
+  uint32_t ngroups = pl.nb / pl.group;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint32_t)pl.nwin * ngroups) return;
+  uint32_t w = t / ngroups, g = t % ngroups;
+  const XYZZ<F>* B = buckets + (uint64_t)w * pl.nb + (uint64_t)g * pl.group;
+  XYZZ<F> run, acc;
+  E::set_inf(run);
+  E::set_inf(acc);
+  for (int k = (int)pl.group - 1; k >= 0; k--) {
+    XYZZ<F> b;
+    load16_rw(b, B + k);
+    E::add(run, b);
+    E::add(acc, run);
+  }
+  // bucket k of this group has weight g*group + k + 1 ; acc holds sum (k+1) B_k, run holds sum B_k
+  uint32_t base = g * pl.group;
+  if (base) {
+    XYZZ<F> m;
+    E::mul_u32(m, run, base);
+    E::add(acc, m);
+  }
+  store16(groups + t, acc);
+}
+
+// one block per window: windows[w] = sum over its groups
+template <class F>
+__global__ void __launch_bounds__(kReduceThreads)
+k_msm_window_sum(const XYZZ<F>* __restrict__ groups, MsmPlan pl, XYZZ<F>* __restrict__ windows) {
+  extern __shared__ uint4 smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  using E = EC<F>;
+  uint32_t ngroups = pl.nb / pl.group;
+  const XYZZ<F>* G = groups + (uint64_t)blockIdx.x * ngroups;
+  XYZZ<F> acc;
+  E::set_inf(acc);
+  for (uint32_t g = threadIdx.x; g < ngroups; g += kReduceThreads) {
+    XYZZ<F> p;
+    load16_rw(p, G + g);
+    E::add(acc, p);
+  }
+  block_sum<F, kReduceThreads>(acc, sm);
+  if (threadIdx.x == 0) store16(windows + blockIdx.x, acc);
+}
+
+// result = sum_w 2^(c w) windows[w]   (single thread; latency hidden by the other MSM streams)
+template <class F>
+__global__ void k_msm_horner(const XYZZ<F>* __restrict__ windows, MsmPlan pl, XYZZ<F>* __restrict__ out) {
+  using E = EC<F>;
+  if (threadIdx.x || blockIdx.x) return;
+  XYZZ<F> acc;
+  E::set_inf(acc);
+  for (int w = pl.nwin - 1; w >= 0; w--) {
+    for (int i = 0; i < pl.c; i++) E::dbl(acc);
+    XYZZ<F> ws;
+    load16_rw(ws, windows + w);
+    E::add(acc, ws);
+  }
+  store16(out, acc);
+}
+
+}  // namespace b200

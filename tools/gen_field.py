@@ -1,0 +1,374 @@
+#!/usr/bin/env python3
+"""Generator for the sm_100a Montgomery field kernels (32-bit limbs, IMAD.WIDE carry chains).
+
+Every field operation is built as a straight-line program over a tiny IR whose
+ops are exactly PTX integer instructions with explicit carry-flag semantics
+(`mad.lo.cc.u32`, `madc.hi.cc.u32`, `addc.cc.u32`, ...).  The same op list is
+
+  * emitted as ONE inline-asm block per field operation (the carry flag never
+    lives across an asm boundary, moduli are immediates so they cost no
+    registers), and
+  * interpreted in Python (`run`) so the exact instruction sequence is checked
+    against big-integer arithmetic on a machine without a GPU
+    (tests/test_field_ir.py).
+
+Layout contract: an element is N little-endian uint32 limbs holding x*R mod p,
+R = 2^(32N) - bit-identical to gnark-crypto's `[N/2]uint64` Montgomery elements
+(SURVEY.md A.4), so proving-key memory is consumed without conversion.
+
+Usage:  python tools/gen_field.py <out_dir>
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+MASK = 0xFFFFFFFF
+
+
+# ----------------------------------------------------------------------------- IR
+class Prog:
+    """Straight-line program.  Operands are register names (str) or immediates (int)."""
+
+    def __init__(self, name, inputs, n_out):
+        self.name = name
+        self.inputs = list(inputs)          # input register names
+        self.outputs = ["o%d" % i for i in range(n_out)]
+        self.ops = []
+        self.temps = []
+        self._n = 0
+
+    def tmp(self):
+        t = "t%d" % self._n
+        self._n += 1
+        self.temps.append(t)
+        return t
+
+    def op(self, opc, d, *srcs):
+        self.ops.append((opc, d) + tuple(srcs))
+        return d
+
+    # --- interpreter (PTX semantics, CC.CF modelled explicitly)
+    def run(self, in_vals):
+        reg = dict(zip(self.inputs, in_vals))
+        cf = 0
+
+        def v(x):
+            return x & MASK if isinstance(x, int) else reg[x]
+
+        for ins in self.ops:
+            opc, d, s = ins[0], ins[1], ins[2:]
+            base = opc.split(".")[0]
+            cc_out = opc.endswith(".cc")
+            cin = base in ("addc", "subc", "madc")
+            if base in ("add", "addc"):
+                t = v(s[0]) + v(s[1]) + (cf if cin else 0)
+                if cc_out:
+                    cf = t >> 32
+                reg[d] = t & MASK
+            elif base in ("sub", "subc"):
+                t = v(s[0]) - v(s[1]) - (cf if cin else 0)
+                if cc_out:
+                    cf = 1 if t < 0 else 0
+                reg[d] = t & MASK
+            elif base in ("mad", "madc"):
+                prod = v(s[0]) * v(s[1])
+                part = (prod & MASK) if ".lo" in opc else (prod >> 32)
+                t = part + v(s[2]) + (cf if cin else 0)
+                if cc_out:
+                    cf = t >> 32
+                reg[d] = t & MASK
+            elif base == "mul":
+                prod = v(s[0]) * v(s[1])
+                reg[d] = (prod & MASK) if ".lo" in opc else (prod >> 32)
+            elif base == "mov":
+                reg[d] = v(s[0])
+            elif base == "selp":       # d = s[2] != 0 ? s[0] : s[1]   (emitted as setp + selp)
+                reg[d] = v(s[0]) if v(s[2]) != 0 else v(s[1])
+            elif base == "or":
+                reg[d] = v(s[0]) | v(s[1])
+            else:
+                raise ValueError(opc)
+        return [reg[o] for o in self.outputs]
+
+    # --- PTX emission
+    def emit_asm(self, indent="    "):
+        """Return (asm_text_lines, n_outputs, n_inputs); placeholders: outputs first."""
+        ph = {}
+        k = 0
+        for o in self.outputs:
+            ph[o] = "%%%d" % k
+            k += 1
+        for i in self.inputs:
+            ph[i] = "%%%d" % k
+            k += 1
+
+        def f(x):
+            if isinstance(x, int):
+                return "0x%08x" % (x & MASK)
+            return ph.get(x, x)
+
+        lines = ["{"]
+        # temps in chunks
+        for i in range(0, len(self.temps), 16):
+            lines.append(".reg .u32 " + ", ".join(self.temps[i:i + 16]) + ";")
+        if any(o[0].startswith("selp") for o in self.ops):
+            lines.append(".reg .pred pq;")
+        for ins in self.ops:
+            opc, d, s = ins[0], ins[1], ins[2:]
+            if opc == "selp":
+                lines.append("setp.ne.u32 pq, %s, 0;" % f(s[2]))
+                lines.append("selp.u32 %s, %s, %s, pq;" % (f(d), f(s[0]), f(s[1])))
+            elif opc == "or":
+                lines.append("or.b32 %s, %s;" % (f(d), ", ".join(f(x) for x in s)))
+            else:
+                lines.append("%s.u32 %s, %s;" % (opc, f(d), ", ".join(f(x) for x in s)))
+        lines.append("}")
+        return lines
+
+
+def limbs(x, n):
+    return [(x >> (32 * i)) & MASK for i in range(n)]
+
+
+def from_limbs(v):
+    return sum(int(x) << (32 * i) for i, x in enumerate(v))
+
+
+# ----------------------------------------------------------------------------- programs
+def _cond_sub_p(P, T, p_l, outs):
+    """outs = T - p if T >= p else T   (T < 2p < 2^(32N))."""
+    n = len(T)
+    U = [P.tmp() for _ in range(n)]
+    P.op("sub.cc", U[0], T[0], p_l[0])
+    for k in range(1, n):
+        P.op("subc.cc", U[k], T[k], p_l[k])
+    bw = P.tmp()
+    P.op("subc", bw, 0, 0)                      # 0xffffffff when T < p
+    for k in range(n):
+        P.op("selp", outs[k], T[k], U[k], bw)
+
+
+def prog_add(n, p):
+    A = ["a%d" % i for i in range(n)]
+    B = ["b%d" % i for i in range(n)]
+    P = Prog("add", A + B, n)
+    p_l = limbs(p, n)
+    T = [P.tmp() for _ in range(n)]
+    P.op("add.cc", T[0], A[0], B[0])
+    for k in range(1, n - 1):
+        P.op("addc.cc", T[k], A[k], B[k])
+    P.op("addc", T[n - 1], A[n - 1], B[n - 1])
+    _cond_sub_p(P, T, p_l, P.outputs)
+    return P
+
+
+def prog_sub(n, p):
+    A = ["a%d" % i for i in range(n)]
+    B = ["b%d" % i for i in range(n)]
+    P = Prog("sub", A + B, n)
+    p_l = limbs(p, n)
+    T = [P.tmp() for _ in range(n)]
+    P.op("sub.cc", T[0], A[0], B[0])
+    for k in range(1, n):
+        P.op("subc.cc", T[k], A[k], B[k])
+    bw = P.tmp()
+    P.op("subc", bw, 0, 0)                      # all-ones when a < b
+    U = [P.tmp() for _ in range(n)]
+    P.op("add.cc", U[0], T[0], p_l[0])
+    for k in range(1, n - 1):
+        P.op("addc.cc", U[k], T[k], p_l[k])
+    P.op("addc", U[n - 1], T[n - 1], p_l[n - 1])
+    for k in range(n):
+        P.op("selp", P.outputs[k], U[k], T[k], bw)
+    return P
+
+
+def _reduce_row(P, X, Y, p_l, m0):
+    """X (pos 0..n-1) / Y (pos 1..n): add m*p so that X[0] becomes 0."""
+    n = len(X)
+    m = P.tmp()
+    # m0 == 2^32-1 would let ptxas rewrite m = -X[0] and fold the negation into the modulus
+    # immediates of the lo half only, which blocks IMAD.WIDE fusion - keep it opaque instead.
+    P.op("mul.lo", m, X[0], "m0r" if (m0 == MASK and "m0r" in P.inputs) else m0)
+    # odd limbs of p into Y
+    for j in range(0, n, 2):
+        P.op("mad.lo.cc" if j == 0 else "madc.lo.cc", Y[j], m, p_l[j + 1], Y[j])
+        P.op("madc.hi.cc" if j + 2 < n else "madc.hi", Y[j + 1], m, p_l[j + 1], Y[j + 1])
+    # even limbs of p into X
+    for j in range(0, n, 2):
+        P.op("mad.lo.cc" if j == 0 else "madc.lo.cc", X[j], m, p_l[j], X[j])
+        P.op("madc.hi.cc", X[j + 1], m, p_l[j], X[j + 1])
+    P.op("addc", Y[n - 1], Y[n - 1], 0)
+
+
+def prog_mul(n, p, b_is_a=False):
+    """Montgomery product a*b/R mod p, even/odd column accumulation (2n^2+n wide MACs)."""
+    assert n % 2 == 0
+    A = ["a%d" % i for i in range(n)]
+    B = A if b_is_a else ["b%d" % i for i in range(n)]
+    m0 = (-pow(p, -1, 1 << 32)) & MASK
+    extra = ["m0r"] if m0 == MASK else []
+    P = Prog("sqr" if b_is_a else "mul", (A if b_is_a else A + B) + extra, n)
+    p_l = limbs(p, n)
+    X = [P.tmp() for _ in range(n)]
+    Y = [P.tmp() for _ in range(n)]
+    for j in range(0, n, 2):
+        P.op("mul.lo", X[j], A[j], B[0])
+        P.op("mul.hi", X[j + 1], A[j], B[0])
+    for j in range(0, n, 2):
+        P.op("mul.lo", Y[j], A[j + 1], B[0])
+        P.op("mul.hi", Y[j + 1], A[j + 1], B[0])
+    _reduce_row(P, X, Y, p_l, m0)
+    for i in range(1, n):
+        Xp, X = X, Y                               # shift by one limb: old odd column becomes even
+        Y = [P.tmp() for _ in range(n)]
+        P.op("add.cc", X[0], X[0], Xp[1])
+        for j in range(0, n, 2):
+            lo_add = Xp[j + 2] if j + 2 < n else 0
+            hi_add = Xp[j + 3] if j + 3 < n else 0
+            P.op("madc.lo.cc", Y[j], A[j + 1], B[i], lo_add)
+            P.op("madc.hi.cc" if j + 2 < n else "madc.hi", Y[j + 1], A[j + 1], B[i], hi_add)
+        for j in range(0, n, 2):
+            P.op("mad.lo.cc" if j == 0 else "madc.lo.cc", X[j], A[j], B[i], X[j])
+            P.op("madc.hi.cc", X[j + 1], A[j], B[i], X[j + 1])
+        P.op("addc", Y[n - 1], Y[n - 1], 0)
+        _reduce_row(P, X, Y, p_l, m0)
+    T = [P.tmp() for _ in range(n)]
+    P.op("add.cc", T[0], X[1], Y[0])
+    for k in range(1, n - 1):
+        P.op("addc.cc", T[k], X[k + 1], Y[k])
+    P.op("addc", T[n - 1], Y[n - 1], 0)
+    _cond_sub_p(P, T, p_l, P.outputs)
+    return P
+
+
+def prog_from_mont(n, p):
+    """a / R mod p  (Montgomery reduction of a single-width value; n^2+n wide MACs)."""
+    A = ["a%d" % i for i in range(n)]
+    m0 = (-pow(p, -1, 1 << 32)) & MASK
+    P = Prog("from_mont", A + (["m0r"] if m0 == MASK else []), n)
+    p_l = limbs(p, n)
+    X = [P.tmp() for _ in range(n)]
+    Y = [P.tmp() for _ in range(n)]
+    for k in range(n):
+        P.op("mov", X[k], A[k])
+        P.op("mov", Y[k], 0)
+    _reduce_row(P, X, Y, p_l, m0)
+    for i in range(1, n):
+        Xp, X = X, Y
+        Y = [P.tmp() for _ in range(n)]
+        P.op("add.cc", X[0], X[0], Xp[1])
+        for k in range(n):
+            src = Xp[k + 2] if k + 2 < n else 0
+            P.op("addc.cc" if k < n - 1 else "addc", Y[k], src, 0)
+        _reduce_row(P, X, Y, p_l, m0)
+    T = [P.tmp() for _ in range(n)]
+    P.op("add.cc", T[0], X[1], Y[0])
+    for k in range(1, n - 1):
+        P.op("addc.cc", T[k], X[k + 1], Y[k])
+    P.op("addc", T[n - 1], Y[n - 1], 0)
+    _cond_sub_p(P, T, p_l, P.outputs)
+    return P
+
+
+# ----------------------------------------------------------------------------- fields
+def field_table():
+    from oracle import params as PR
+    return [
+        ("bn254_fp", PR.BN254.p, 8),
+        ("bn254_fr", PR.BN254.r, 8),
+        ("bls12_377_fp", PR.BLS12_377.p, 12),
+        ("bls12_377_fr", PR.BLS12_377.r, 8),
+        ("bls12_381_fp", PR.BLS12_381.p, 12),
+        ("bls12_381_fr", PR.BLS12_381.r, 8),
+        ("bw6_761_fp", PR.BW6_761.p, 24),
+        # bw6_761_fr == bls12_377_fp (same modulus): aliased in field.cuh
+    ]
+
+
+def programs(n, p):
+    return {
+        "add": prog_add(n, p),
+        "sub": prog_sub(n, p),
+        "mul": prog_mul(n, p),
+        "sqr": prog_mul(n, p, b_is_a=True),
+        "from_mont": prog_from_mont(n, p),
+    }
+
+
+def emit_fn(prog, fname, n, arity):
+    """C++ wrapper: static __device__ void fname(uint32_t* r, const uint32_t* a[, const uint32_t* b])."""
+    lines = prog.emit_asm()
+    args = "uint32_t* __restrict__ r, const uint32_t* a" + (", const uint32_t* b" if arity == 2 else "")
+    out = ["  static __device__ __forceinline__ void %s(%s) {" % (fname, args)]
+    # outputs go to fresh locals so r may alias a / b
+    out.append("    uint32_t " + ", ".join("o%d" % i for i in range(n)) + ";")
+    out.append("    asm(")
+    for ln in lines:
+        out.append('      "%s\\n\\t"' % ln)
+    outs = ", ".join('"=r"(o%d)' % i for i in range(n))
+    ins = ", ".join('"r"(a[%d])' % i for i in range(n))
+    if arity == 2:
+        ins += ", " + ", ".join('"r"(b[%d])' % i for i in range(n))
+    if "m0r" in prog.inputs:
+        ins += ', "r"(k_m0_opaque[0])'
+    out.append("      : %s" % outs)
+    out.append("      : %s);" % ins)
+    out.append("    " + " ".join("r[%d] = o%d;" % (i, i) for i in range(n)))
+    out.append("  }")
+    return "\n".join(out)
+
+
+def emit_field(name, p, n):
+    progs = programs(n, p)
+    R = 1 << (32 * n)
+    hdr = []
+    hdr.append("// GENERATED by tools/gen_field.py - do not edit.  Field %s, %d x 32-bit limbs." % (name, n))
+    hdr.append("#pragma once")
+    hdr.append("#include <stdint.h>")
+    hdr.append("namespace b200 {")
+    hdr.append("#ifndef B200_M0_OPAQUE_DEFINED")
+    hdr.append("#define B200_M0_OPAQUE_DEFINED")
+    hdr.append("// read through the constant bank so ptxas cannot see that M0 == 2^32-1 (see gen_field.py)")
+    hdr.append("static __device__ __constant__ uint32_t k_m0_opaque[1] = {0xffffffffu};")
+    hdr.append("#endif")
+    hdr.append("struct %s {" % name)
+    hdr.append("  static constexpr int N = %d;" % n)
+    hdr.append("  static constexpr int BITS = %d;" % p.bit_length())
+
+    def arr(label, val):
+        return "  static __device__ __host__ __forceinline__ uint32_t %s(int i) { constexpr uint32_t v[%d] = {%s}; return v[i]; }" % (
+            label, n, ", ".join("0x%08xu" % x for x in limbs(val, n)))
+
+    hdr.append(arr("modulus", p))
+    hdr.append(arr("one", R % p))             # Montgomery form of 1
+    hdr.append(arr("r2", (R * R) % p))        # to-Montgomery multiplier
+    hdr.append(arr("r3", (R * R * R) % p))
+    hdr.append("  static constexpr uint32_t M0 = 0x%08xu;" % ((-pow(p, -1, 1 << 32)) & MASK))
+    hdr.append(emit_fn(progs["add"], "add", n, 2))
+    hdr.append(emit_fn(progs["sub"], "sub", n, 2))
+    hdr.append(emit_fn(progs["mul"], "mul", n, 2))
+    hdr.append(emit_fn(progs["sqr"], "sqr", n, 1))
+    hdr.append(emit_fn(progs["from_mont"], "from_mont", n, 1))
+    hdr.append("};")
+    hdr.append("}  // namespace b200")
+    return "\n".join(hdr) + "\n"
+
+
+def main():
+    out_dir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(
+        os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "davinci-node_b200", "csrc", "gen")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, p, n in field_table():
+        path = os.path.join(out_dir, "field_%s.cuh" % name)
+        txt = emit_field(name, p, n)
+        old = open(path).read() if os.path.exists(path) else None
+        if old != txt:
+            with open(path, "w") as fh:
+                fh.write(txt)
+        print("generated", path, "(%d limbs)" % n)
+
+
+if __name__ == "__main__":
+    main()
