@@ -24,7 +24,48 @@ lib = _load()
 
 _vp, _u64, _u32, _i = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
 
+
+
+class Slice(C.Structure):
+    _fields_ = [("ptr", _vp), ("len", _u64)]
+
+
+class PkDesc(C.Structure):
+    _fields_ = [
+        ("curve", _i), ("domain_size", _u64), ("generator", _vp), ("coset_gen", _vp),
+        ("g1_alpha", _vp), ("g1_beta", _vp), ("g1_delta", _vp),
+        ("g1_A", Slice), ("g1_B", Slice), ("g1_Z", Slice), ("g1_K", Slice),
+        ("g2_beta", _vp), ("g2_delta", _vp), ("g2_B", Slice),
+        ("infinity_a", Slice), ("infinity_b", Slice),
+        ("nb_wires", _u64), ("nb_public", _u64), ("krs_skip", Slice),
+        ("nb_commitments", _u32), ("commit_basis", C.POINTER(Slice)), ("commit_basis_exp_sigma", C.POINTER(Slice)),
+    ]
+
+
+class ProveIn(C.Structure):
+    _fields_ = [
+        ("wires", Slice), ("a", Slice), ("b", Slice), ("c", Slice), ("r", _vp), ("s", _vp),
+        ("nb_commitments", _u32), ("priv_committed", C.POINTER(Slice)), ("fold_challenge", _vp),
+    ]
+
+
+class ProofOut(C.Structure):
+    _fields_ = [("ar", _vp), ("bs", _vp), ("krs", _vp), ("pok", _vp)]
+
+
 _PROTOS = {
+    "b200_domain_create": (_i, [_i, _u64, _vp, _vp, C.POINTER(_u64)]),
+    "b200_domain_release": (_i, [_u64]),
+    "b200_ntt_dev": (_i, [_u64, _vp, _i, _i, _i, _vp]),
+    "b200_compute_h_dev": (_i, [_u64, _vp, _vp, _vp, _vp]),
+    "b200_pk_register": (_i, [C.POINTER(PkDesc), C.POINTER(_u64)]),
+    "b200_pk_release": (_i, [_u64]),
+    "b200_commit": (_i, [_u64, _u32, Slice, _vp, _i]),
+    "b200_prove": (_i, [_u64, C.POINTER(ProveIn), C.POINTER(ProofOut), _i]),
+    "b200_prove_dev": (_i, [_u64, C.POINTER(ProveIn), C.POINTER(ProofOut), _i]),
+    "b200_kzg_srs_register": (_i, [_vp, _u32, C.POINTER(_u64)]),
+    "b200_kzg_srs_release": (_i, [_u64]),
+    "b200_blob_commit": (_i, [_u64, _vp, _vp, _i]),
     "b200_init": (_i, [_u32]),
     "b200_device_count": (_i, []),
     "b200_last_error": (C.c_char_p, []),
@@ -55,8 +96,18 @@ def check(status):
         raise B200Error(lib.b200_last_error().decode("utf-8", "replace"))
 
 
+_inited = False
+
+
 def init(device_mask=0):
+    global _inited
     check(lib.b200_init(device_mask))
+    _inited = True
+
+
+def init_once():
+    if not _inited:
+        init(int(os.environ.get("B200_DEVICE_MASK", "0"), 0))
 
 
 def msm_plan(curve, n, window_bits=0):

@@ -62,7 +62,31 @@ enum FieldSel { FIELD_FP = 0, FIELD_FR = 1, FIELD_FP2 = 2 };
 enum FieldOp { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_SQR = 3, OP_FROM_MONT = 4, OP_TO_MONT = 5, OP_INV = 6, OP_NEG = 7 };
 enum EcOp { EC_MADD = 0, EC_ADD = 1, EC_DBL = 2, EC_TO_AFFINE = 3, EC_MUL_SCALAR = 4 };
 
-struct NttWorkspace;
+// Device-resident evaluation domain of size 2^logn (twiddle / coset-power tables live in HBM).
+struct NttDomain {
+  int logn = 0;
+  int lo_bits = 0;      // split of the two-level coset power tables
+  DevBuf tw_fwd, tw_inv;               // omega^k, omega^-k   (k < n/2)
+  DevBuf g_lo, g_hi, g_hi_scaled;      // g^j ; g^(j 2^lo_bits) ; same times 1/n
+  DevBuf gi_lo, gi_hi_scaled;          // g^-j ; g^-(j 2^lo_bits) / n
+  DevBuf consts;                       // [omega^-1, g^-1, 1/n, 1/(g^n-1), omega, g]
+};
+
+// Inputs of the final proof assembly (all device pointers, XYZZ points unless noted).
+struct AssembleArgs {
+  const void* ar_msm;     // sum w_i A_i + alpha + r delta      (G1)
+  const void* bs1_msm;    // sum w_i B_i + beta + s delta       (G1)
+  const void* bs2_msm;    // same in G2
+  const void* k_msm;      // sum w_i K_i - r s delta            (G1)
+  const void* z_msm;      // sum h_i Z_i                        (G1)
+  const void* pok_msm;    // may be null                        (G1)
+  const void* rs;         // 4 Fr elements (Montgomery): r, s, 1, -r s
+  void* tmp;              // 2 G1 XYZZ scratch
+  void* out_ar;           // G1 affine
+  void* out_bs;           // G2 affine
+  void* out_krs;          // G1 affine
+  void* out_pok;          // G1 affine (if pok_msm)
+};
 
 // One implementation per curve (template instantiation in curve_<name>.cu).
 struct CurveBackend {
@@ -76,8 +100,24 @@ struct CurveBackend {
   virtual int fr_bits() const = 0;
 
   // --- MSM: device pointers, result (one XYZZ point) written to d_out; fully asynchronous on `s`
+  // d_index_map (optional): scalar i multiplies points[map[i]]; map[i] == 0xffffffff skips scalar i
   virtual void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out_xyzz,
-                   MsmWorkspace& ws, cudaStream_t s, int c_override, MsmStats* stats) = 0;
+                   MsmWorkspace& ws, cudaStream_t s, int c_override, MsmStats* stats,
+                   const uint32_t* d_index_map = nullptr) = 0;
+  // --- NTT / quotient
+  virtual void domain_init(NttDomain& d, int logn, const void* d_omega, const void* d_g, cudaStream_t s) = 0;
+  // gnark fft.Domain semantics: inverse ? FFTInverse : FFT ; dit ? DIT (bit-reversed in) : DIF ; coset
+  virtual void ntt(NttDomain& d, void* d_data, bool inverse, bool dit, bool coset, cudaStream_t s) = 0;
+  // a <- h = ((a*b - c) / Z) coefficients in bit-reversed order (gnark computeH); a, b, c natural order, length n
+  virtual void compute_h(NttDomain& d, void* d_a, void* d_b, void* d_c, cudaStream_t s) = 0;
+  virtual void scale_vec(void* d_x, const void* d_c, uint64_t n, cudaStream_t s) = 0;
+  // writes r, s, 1, -r*s (Montgomery) to d_out[0..4) from canonical-or-Montgomery inputs already on device
+  virtual void prep_rs(const void* d_r, const void* d_s, void* d_out4, cudaStream_t s) = 0;
+  virtual void assemble(const AssembleArgs& a, cudaStream_t s) = 0;
+  // --- EIP-4844 helpers (BLS12-381 only; other curves throw)
+  virtual void g1_decompress(const void* d_bytes, void* d_affine, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;
+  virtual void g1_compress(const void* d_affine, void* d_bytes, uint32_t n, cudaStream_t s) = 0;
+  virtual void blob_to_scalars(const void* d_blob, void* d_scalars, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;
   // --- point helpers
   virtual void to_affine(int group, const void* d_xyzz, void* d_affine, uint32_t count, cudaStream_t s) = 0;
   // out = sum_i [k_i] P_i  (tiny, single thread): used for the alpha/beta/delta terms of the proof

@@ -10,6 +10,7 @@
 
 #include "backend.h"
 #include "msm_plan.h"
+#include "prover.h"
 
 using namespace b200;
 
@@ -80,6 +81,41 @@ struct ScopedStream {
     if (s) cudaStreamDestroy(s);
   }
 };
+
+// ---- handle registries
+struct DomainHandle {
+  CurveBackend* cb;
+  int device;
+  NttDomain dom;
+};
+std::mutex g_hmu;
+uint64_t g_next_handle = 1;
+std::map<uint64_t, std::unique_ptr<DomainHandle>> g_domains;
+std::map<uint64_t, std::shared_ptr<ProvingKeyDev>> g_pks;
+std::map<uint64_t, std::shared_ptr<KzgSrsDev>> g_srs;
+
+std::vector<int> selected_devices() {
+  int n = 0;
+  B200_CUDA(cudaGetDeviceCount(&n));
+  if (n == 0) throw std::runtime_error("no CUDA device visible (this backend has no CPU fallback)");
+  uint32_t mask;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    mask = g_inited ? g_mask : 0xffffffffu;
+  }
+  std::vector<int> v;
+  for (int d = 0; d < n && d < 32; d++)
+    if (mask & (1u << d)) v.push_back(d);
+  if (v.empty()) throw std::runtime_error("device mask selects no visible GPU");
+  return v;
+}
+
+std::shared_ptr<ProvingKeyDev> find_pk(uint64_t h) {
+  std::lock_guard<std::mutex> lk(g_hmu);
+  auto it = g_pks.find(h);
+  if (it == g_pks.end()) throw std::runtime_error("unknown proving-key handle");
+  return it->second;
+}
 
 struct ScopedDev {
   void* p = nullptr;
@@ -193,6 +229,128 @@ int b200_dbg_ec_op_dev(int curve_id, int group, int op, const void* a, const voi
 
 int b200_calib_mul_dev(int curve_id, int field, void* d_inout, uint64_t nthreads, int iters, void* stream) {
   return guarded([&] { curve(curve_id).calib_mul(field, d_inout, nthreads, iters, (cudaStream_t)stream); });
+}
+
+// ---------------------------------------------------------------------------------- NTT
+int b200_domain_create(int curve_id, uint64_t size, const void* generator, const void* coset_gen, uint64_t* out) {
+  return guarded([&] {
+    CurveBackend& cb = curve(curve_id);
+    if (!generator || !coset_gen || !out) throw std::runtime_error("null argument");
+    int logn = 0;
+    while ((1ull << logn) < size) logn++;
+    if ((1ull << logn) != size) throw std::runtime_error("domain size must be a power of two");
+    std::unique_ptr<DomainHandle> h(new DomainHandle());
+    h->cb = &cb;
+    h->device = current_device();
+    ScopedStream st;
+    ScopedDev gens(2 * cb.fr_bytes());
+    B200_CUDA(cudaMemcpyAsync(gens.p, generator, cb.fr_bytes(), cudaMemcpyHostToDevice, st.s));
+    B200_CUDA(cudaMemcpyAsync((uint8_t*)gens.p + cb.fr_bytes(), coset_gen, cb.fr_bytes(), cudaMemcpyHostToDevice, st.s));
+    cb.domain_init(h->dom, logn, gens.p, (uint8_t*)gens.p + cb.fr_bytes(), st.s);
+    B200_CUDA(cudaStreamSynchronize(st.s));
+    std::lock_guard<std::mutex> lk(g_hmu);
+    *out = g_next_handle++;
+    g_domains[*out] = std::move(h);
+  });
+}
+
+int b200_domain_release(uint64_t h) {
+  return guarded([&] {
+    std::lock_guard<std::mutex> lk(g_hmu);
+    if (!g_domains.erase(h)) throw std::runtime_error("unknown domain handle");
+  });
+}
+
+static DomainHandle& find_domain(uint64_t h) {
+  std::lock_guard<std::mutex> lk(g_hmu);
+  auto it = g_domains.find(h);
+  if (it == g_domains.end()) throw std::runtime_error("unknown domain handle");
+  return *it->second;
+}
+
+int b200_ntt_dev(uint64_t domain, void* d_data, int inverse, int decimation, int coset, void* stream) {
+  return guarded([&] {
+    DomainHandle& h = find_domain(domain);
+    h.cb->ntt(h.dom, d_data, inverse != 0, decimation != 0, coset != 0, (cudaStream_t)stream);
+  });
+}
+
+int b200_compute_h_dev(uint64_t domain, void* d_a, void* d_b, void* d_c, void* stream) {
+  return guarded([&] {
+    DomainHandle& h = find_domain(domain);
+    h.cb->compute_h(h.dom, d_a, d_b, d_c, (cudaStream_t)stream);
+  });
+}
+
+// ---------------------------------------------------------------------------------- Groth16
+int b200_pk_register(const b200_pk_desc* desc, uint64_t* handle_out) {
+  return guarded([&] {
+    if (!desc || !handle_out) throw std::runtime_error("null argument");
+    std::shared_ptr<ProvingKeyDev> pk(ProvingKeyDev::create(*desc, selected_devices()).release());
+    std::lock_guard<std::mutex> lk(g_hmu);
+    *handle_out = g_next_handle++;
+    g_pks[*handle_out] = pk;
+  });
+}
+
+int b200_pk_release(uint64_t h) {
+  return guarded([&] {
+    std::lock_guard<std::mutex> lk(g_hmu);
+    if (!g_pks.erase(h)) throw std::runtime_error("unknown proving-key handle");
+  });
+}
+
+int b200_commit(uint64_t h, uint32_t i, b200_slice values, void* out, int device) {
+  return guarded([&] {
+    if (!out) throw std::runtime_error("null output");
+    find_pk(h)->commit(i, values, out, device);
+  });
+}
+
+int b200_prove(uint64_t h, const b200_prove_in* in, const b200_proof_out* out, int device) {
+  return guarded([&] {
+    if (!in || !out || !out->ar || !out->bs || !out->krs) throw std::runtime_error("null argument");
+    find_pk(h)->prove(*in, *out, device, false);
+  });
+}
+
+int b200_prove_dev(uint64_t h, const b200_prove_in* in, const b200_proof_out* out, int device) {
+  return guarded([&] {
+    if (!in || !out || !out->ar || !out->bs || !out->krs) throw std::runtime_error("null argument");
+    find_pk(h)->prove(*in, *out, device, true);
+  });
+}
+
+// ---------------------------------------------------------------------------------- KZG
+int b200_kzg_srs_register(const uint8_t* g1_lagrange, uint32_t npoints, uint64_t* handle_out) {
+  return guarded([&] {
+    if (!g1_lagrange || !handle_out) throw std::runtime_error("null argument");
+    std::shared_ptr<KzgSrsDev> srs(KzgSrsDev::create(g1_lagrange, npoints, selected_devices()).release());
+    std::lock_guard<std::mutex> lk(g_hmu);
+    *handle_out = g_next_handle++;
+    g_srs[*handle_out] = srs;
+  });
+}
+
+int b200_kzg_srs_release(uint64_t h) {
+  return guarded([&] {
+    std::lock_guard<std::mutex> lk(g_hmu);
+    if (!g_srs.erase(h)) throw std::runtime_error("unknown SRS handle");
+  });
+}
+
+int b200_blob_commit(uint64_t h, const uint8_t* blob, uint8_t commitment_out[48], int device) {
+  return guarded([&] {
+    if (!blob || !commitment_out) throw std::runtime_error("null argument");
+    std::shared_ptr<KzgSrsDev> srs;
+    {
+      std::lock_guard<std::mutex> lk(g_hmu);
+      auto it = g_srs.find(h);
+      if (it == g_srs.end()) throw std::runtime_error("unknown SRS handle");
+      srs = it->second;
+    }
+    srs->blob_commit(blob, commitment_out, device);
+  });
 }
 
 }  // extern "C"

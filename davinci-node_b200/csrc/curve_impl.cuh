@@ -7,6 +7,7 @@
 #include "backend.h"
 #include "msm.cuh"
 #include "ntt.cuh"
+#include "kzg.cuh"
 
 namespace b200 {
 
@@ -104,10 +105,66 @@ __global__ void __launch_bounds__(256) k_calib_mul(typename F::El* io, uint64_t 
   io[i] = x;
 }
 
+// ------------------------------------------------------------------------------------ proof assembly
+// out4 = {r, s, 1, -r*s} in Montgomery form
+template <class Fr>
+__global__ void k_prep_rs(const typename Fr::El* r, const typename Fr::El* s, typename Fr::El* out4) {
+  typename Fr::El t;
+  out4[0] = *r;
+  out4[1] = *s;
+  Fr::set_one(out4[2]);
+  Fr::mul(t, *r, *s);
+  Fr::neg(out4[3], t);
+}
+
+// tmp[0] = [s] Ar ; tmp[1] = [r] Bs1      (one thread each)
+template <class F, class Fr>
+__global__ void k_assemble_mul(const XYZZ<F>* ar, const XYZZ<F>* bs1, const typename Fr::El* rs, XYZZ<F>* tmp) {
+  typename Fr::El k;
+  XYZZ<F> p, r;
+  if (blockIdx.x == 0) {
+    Fr::from_mont(k, rs[1]);
+    p = *ar;
+  } else {
+    Fr::from_mont(k, rs[0]);
+    p = *bs1;
+  }
+  EC<F>::template mul_scalar<Fr::N>(r, p, k.v);
+  tmp[blockIdx.x] = r;
+}
+
+// block 0: Krs = K + Z + s*Ar + r*Bs1 -> affine ; 1: Ar -> affine ; 2: Bs (G2) -> affine ; 3: Pok -> affine
+template <class F1, class F2>
+__global__ void k_assemble_out(const XYZZ<F1>* ar, const XYZZ<F2>* bs2, const XYZZ<F1>* k, const XYZZ<F1>* z,
+                               const XYZZ<F1>* pok, const XYZZ<F1>* tmp, Affine<F1>* out_ar, Affine<F2>* out_bs,
+                               Affine<F1>* out_krs, Affine<F1>* out_pok) {
+  if (blockIdx.x == 0) {
+    XYZZ<F1> acc = *k;
+    EC<F1>::add(acc, *z);
+    EC<F1>::add(acc, tmp[0]);
+    EC<F1>::add(acc, tmp[1]);
+    Affine<F1> o;
+    EC<F1>::to_affine(o, acc);
+    *out_krs = o;
+  } else if (blockIdx.x == 1) {
+    Affine<F1> o;
+    EC<F1>::to_affine(o, *ar);
+    *out_ar = o;
+  } else if (blockIdx.x == 2) {
+    Affine<F2> o;
+    EC<F2>::to_affine(o, *bs2);
+    *out_bs = o;
+  } else if (pok && out_pok) {
+    Affine<F1> o;
+    EC<F1>::to_affine(o, *pok);
+    *out_pok = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------ MSM driver
 template <class F, class Fr>
 void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d_out, MsmWorkspace& ws,
-                cudaStream_t s, int c_override, MsmStats* stats) {
+                cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map) {
   using Pt = XYZZ<F>;
   if (n >= (1ull << 31)) throw std::runtime_error("msm: n must be < 2^31");
   MsmPlan pl = make_msm_plan(n, Fr::BITS, c_override);
@@ -135,9 +192,9 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   const auto* sc = reinterpret_cast<const typename Fr::El*>(d_scalars);
   const auto* pts = reinterpret_cast<const Affine<F>*>(d_points);
   const unsigned sblocks = (unsigned)((n + 255) / 256);
-  k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist);
+  k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, d_index_map);
   k_msm_scan<<<pl.nwin, 1024, 0, s>>>(hist, pl, off, cur);
-  k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted);
+  k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, d_index_map);
   k_msm_accumulate<F><<<(unsigned)((total_b + 127) / 128), 128, 0, s>>>(pts, sorted, off, cur, pl, buckets, tasks,
                                                                          obuckets, ctr);
   // oversized buckets (skewed scalar distributions, e.g. the many 1-valued witness wires)
@@ -169,9 +226,149 @@ struct CurveImpl : CurveBackend {
   int fr_bits() const override { return Fr::BITS; }
 
   void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out, MsmWorkspace& ws,
-           cudaStream_t s, int c_override, MsmStats* stats) override {
-    if (group == 1) msm_launch<G1F, Fr>(d_points, d_scalars, n, d_out, ws, s, c_override, stats);
-    else msm_launch<G2F, Fr>(d_points, d_scalars, n, d_out, ws, s, c_override, stats);
+           cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map) override {
+    if (group == 1) msm_launch<G1F, Fr>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map);
+    else msm_launch<G2F, Fr>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map);
+  }
+
+  // ---------------------------------------------------------------- NTT
+  using FrEl = typename Fr::El;
+  static constexpr int kElogMax = sizeof(FrEl) <= 32 ? 11 : 10;   // tile <= 64 KB (32-B fr) / 48 KB (48-B fr)
+  static constexpr int kStridedMax = 8;
+
+  static std::vector<NttPass> plan_passes(int logn, bool dit) {
+    std::vector<NttPass> v;
+    int lc = std::min(kElogMax, logn);
+    v.push_back(NttPass{logn, 0, lc, 0});
+    int rest = logn - lc;
+    int k = (rest + kStridedMax - 1) / kStridedMax;
+    int s = lc;
+    for (int i = 0; i < k; i++) {
+      int r = (rest + (k - i) - 1) / (k - i);
+      rest -= r;
+      v.push_back(NttPass{logn, s, r, std::min(s, kElogMax - r)});
+      s += r;
+    }
+    if (!dit) std::reverse(v.begin(), v.end());
+    return v;
+  }
+
+  template <bool DIT>
+  static void run_passes(int logn, FrEl* data, const FrEl* tw, NttScale pre, NttScale post, const FrEl* in_b,
+                         const FrEl* in_c, const FrEl* den, cudaStream_t s) {
+    // per-device attribute; cheap enough to set on every call (device pools live in one process)
+    B200_CUDA(cudaFuncSetAttribute(k_ntt_pass<Fr, DIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(sizeof(FrEl) << kElogMax)));
+    auto passes = plan_passes(logn, DIT);
+    const NttScale none{SCALE_NONE, 0, nullptr, nullptr, nullptr};
+    for (size_t i = 0; i < passes.size(); i++) {
+      const NttPass& ps = passes[i];
+      int elog = ps.logr + ps.lo_tile_log;
+      unsigned blocks = 1u << (logn - elog);
+      size_t smem = sizeof(FrEl) << elog;
+      bool first = i == 0, last = i + 1 == passes.size();
+      k_ntt_pass<Fr, DIT><<<blocks, kNttThreads, smem, s>>>(data, tw, ps, first ? pre : none, last ? post : none,
+                                                           first ? in_b : nullptr, first ? in_c : nullptr, den);
+    }
+    B200_CUDA(cudaGetLastError());
+  }
+
+  void domain_init(NttDomain& d, int logn, const void* d_omega, const void* d_g, cudaStream_t s) override {
+    if (logn < 1 || logn > 30) throw std::runtime_error("domain size out of range");
+    d.logn = logn;
+    d.lo_bits = (logn + 1) / 2;
+    const uint64_t n = 1ull << logn, half = n >> 1;
+    const uint64_t nlo = 1ull << d.lo_bits, nhi = 1ull << (logn - d.lo_bits);
+    FrEl* consts = (FrEl*)d.consts.get(6 * sizeof(FrEl));
+    k_domain_consts<Fr><<<1, 1, 0, s>>>(consts, (const FrEl*)d_omega, (const FrEl*)d_g, logn);
+    auto table = [&](DevBuf& buf, const FrEl* base, const FrEl* scale, uint64_t count, uint64_t step) {
+      FrEl* out = (FrEl*)buf.get(count * sizeof(FrEl));
+      k_pow_table<Fr><<<(unsigned)((count + 127) / 128), 128, 0, s>>>(out, base, scale, count, step);
+    };
+    table(d.tw_fwd, consts + 4, nullptr, half, 1);
+    table(d.tw_inv, consts + 0, nullptr, half, 1);
+    table(d.g_lo, consts + 5, nullptr, nlo, 1);
+    table(d.g_hi, consts + 5, nullptr, nhi, nlo);
+    table(d.g_hi_scaled, consts + 5, consts + 2, nhi, nlo);
+    table(d.gi_lo, consts + 1, nullptr, nlo, 1);
+    table(d.gi_hi_scaled, consts + 1, consts + 2, nhi, nlo);
+    B200_CUDA(cudaGetLastError());
+  }
+
+  void ntt(NttDomain& d, void* d_data, bool inverse, bool dit, bool coset, cudaStream_t s) override {
+    const FrEl* consts = (const FrEl*)d.consts.p;
+    NttScale pre{SCALE_NONE, 0, nullptr, nullptr, nullptr}, post = pre;
+    if (!inverse) {
+      if (coset) pre = NttScale{dit ? SCALE_POW_BITREV : SCALE_POW_NATURAL, d.lo_bits, d.g_lo.p, d.g_hi.p, nullptr};
+    } else {
+      if (coset) post = NttScale{dit ? SCALE_POW_NATURAL : SCALE_POW_BITREV, d.lo_bits, d.gi_lo.p, d.gi_hi_scaled.p, nullptr};
+      else post = NttScale{SCALE_CONST, 0, nullptr, nullptr, consts + 2};
+    }
+    const FrEl* tw = (const FrEl*)(inverse ? d.tw_inv.p : d.tw_fwd.p);
+    if (dit) run_passes<true>(d.logn, (FrEl*)d_data, tw, pre, post, nullptr, nullptr, nullptr, s);
+    else run_passes<false>(d.logn, (FrEl*)d_data, tw, pre, post, nullptr, nullptr, nullptr, s);
+  }
+
+  void compute_h(NttDomain& d, void* d_a, void* d_b, void* d_c, cudaStream_t s) override {
+    const FrEl* consts = (const FrEl*)d.consts.p;
+    const NttScale none{SCALE_NONE, 0, nullptr, nullptr, nullptr};
+    const FrEl* twf = (const FrEl*)d.tw_fwd.p;
+    const FrEl* twi = (const FrEl*)d.tw_inv.p;
+    FrEl* v[3] = {(FrEl*)d_a, (FrEl*)d_b, (FrEl*)d_c};
+    // 1. interpolate (unscaled inverse DIF: natural -> bit-reversed coefficients times n)
+    for (int k = 0; k < 3; k++) run_passes<false>(d.logn, v[k], twi, none, none, nullptr, nullptr, nullptr, s);
+    // 2. evaluate on the coset g*<omega>: scale by g^i / n on load, DIT: bit-reversed -> natural
+    NttScale cs{SCALE_POW_BITREV, d.lo_bits, d.g_lo.p, d.g_hi_scaled.p, nullptr};
+    for (int k = 0; k < 3; k++) run_passes<true>(d.logn, v[k], twf, cs, none, nullptr, nullptr, nullptr, s);
+    // 3. (a*b - c) / (g^n - 1) fused into the load of the inverse coset transform; g^-i / n on store
+    NttScale ci{SCALE_POW_BITREV, d.lo_bits, d.gi_lo.p, d.gi_hi_scaled.p, nullptr};
+    run_passes<false>(d.logn, v[0], twi, none, ci, v[1], v[2], consts + 3, s);
+  }
+
+  void g1_decompress(const void* d_bytes, void* d_affine, uint32_t n, uint32_t* d_err, cudaStream_t s) override {
+    if constexpr (Cfg::ID == 3) {
+      k_g1_decompress_bls<Fp><<<(n + 63) / 64, 64, 0, s>>>((const uint8_t*)d_bytes, (Affine<Fp>*)d_affine, n, 4, d_err);
+      B200_CUDA(cudaGetLastError());
+    } else {
+      throw std::runtime_error("g1_decompress: only BLS12-381 (EIP-4844 SRS) is supported");
+    }
+  }
+  void g1_compress(const void* d_affine, void* d_bytes, uint32_t n, cudaStream_t s) override {
+    if constexpr (Cfg::ID == 3) {
+      k_g1_compress_bls<Fp><<<(n + 63) / 64, 64, 0, s>>>((const Affine<Fp>*)d_affine, (uint8_t*)d_bytes, n);
+      B200_CUDA(cudaGetLastError());
+    } else {
+      throw std::runtime_error("g1_compress: only BLS12-381 is supported");
+    }
+  }
+  void blob_to_scalars(const void* d_blob, void* d_scalars, uint32_t n, uint32_t* d_err, cudaStream_t s) override {
+    if constexpr (Cfg::ID == 3) {
+      k_blob_to_scalars<Fr><<<(n + 127) / 128, 128, 0, s>>>((const uint8_t*)d_blob, (FrEl*)d_scalars, n, d_err);
+      B200_CUDA(cudaGetLastError());
+    } else {
+      throw std::runtime_error("blob_to_scalars: only BLS12-381 is supported");
+    }
+  }
+
+  void scale_vec(void* d_x, const void* d_c, uint64_t n, cudaStream_t s) override {
+    if (!n) return;
+    k_scale_vec<Fr><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((FrEl*)d_x, (const FrEl*)d_c, n);
+    B200_CUDA(cudaGetLastError());
+  }
+
+  void prep_rs(const void* d_r, const void* d_s, void* d_out4, cudaStream_t s) override {
+    k_prep_rs<Fr><<<1, 1, 0, s>>>((const FrEl*)d_r, (const FrEl*)d_s, (FrEl*)d_out4);
+    B200_CUDA(cudaGetLastError());
+  }
+
+  void assemble(const AssembleArgs& a, cudaStream_t s) override {
+    using P1 = XYZZ<G1F>;
+    k_assemble_mul<G1F, Fr><<<2, 1, 0, s>>>((const P1*)a.ar_msm, (const P1*)a.bs1_msm, (const FrEl*)a.rs, (P1*)a.tmp);
+    k_assemble_out<G1F, G2F><<<4, 1, 0, s>>>((const P1*)a.ar_msm, (const XYZZ<G2F>*)a.bs2_msm, (const P1*)a.k_msm,
+                                              (const P1*)a.z_msm, (const P1*)a.pok_msm, (const P1*)a.tmp,
+                                              (Affine<G1F>*)a.out_ar, (Affine<G2F>*)a.out_bs,
+                                              (Affine<G1F>*)a.out_krs, (Affine<G1F>*)a.out_pok);
+    B200_CUDA(cudaGetLastError());
   }
 
   void to_affine(int group, const void* d_xyzz, void* d_aff, uint32_t count, cudaStream_t s) override {

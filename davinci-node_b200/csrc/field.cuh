@@ -32,6 +32,32 @@ struct alignas(16) Limbs {
   uint32_t v[N];
 };
 
+// 128-bit vectorised global load / store of POD structs whose size is a multiple of 16 bytes
+template <class T>
+__device__ __forceinline__ void load16(T& dst, const T* src) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte multiple expected");
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(&dst);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = __ldg(s + i);
+}
+template <class T>
+__device__ __forceinline__ void load16_rw(T& dst, const T* src) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(&dst);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+template <class T>
+__device__ __forceinline__ void store16(T* dst, const T& src) {
+  static_assert(sizeof(T) % 16 == 0, "16-byte multiple expected");
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint4* s = reinterpret_cast<const uint4*>(&src);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+}
+
+
 // ---------------------------------------------------------------------------------------- Fp
 template <class P>
 struct FpT {

@@ -51,9 +51,11 @@ __device__ __forceinline__ void for_each_digit(const typename Fr::El& mont, cons
 }
 
 template <class Fr>
-__global__ void k_msm_hist(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ hist) {
+__global__ void k_msm_hist(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ hist,
+                           const uint32_t* __restrict__ index_map) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pl.n) return;
+  if (index_map && index_map[i] == 0xffffffffu) return;
   typename Fr::El s;
   load16(s, scalars + i);
   for_each_digit<Fr>(s, pl, [&](int w, uint32_t b, bool) { atomicAdd(&hist[(uint64_t)w * pl.nb + b], 1u); });
@@ -104,14 +106,19 @@ static __global__ void k_msm_scan(const uint32_t* __restrict__ hist, MsmPlan pl,
 
 template <class Fr>
 __global__ void k_msm_scatter(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ cur,
-                              uint32_t* __restrict__ sorted) {
+                              uint32_t* __restrict__ sorted, const uint32_t* __restrict__ index_map) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pl.n) return;
+  uint32_t pidx = (uint32_t)i;
+  if (index_map) {
+    pidx = index_map[i];
+    if (pidx == 0xffffffffu) return;
+  }
   typename Fr::El s;
   load16(s, scalars + i);
   for_each_digit<Fr>(s, pl, [&](int w, uint32_t b, bool neg) {
     uint32_t pos = atomicAdd(&cur[(uint64_t)w * pl.nb + b], 1u);
-    sorted[(uint64_t)w * pl.n + pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
+    sorted[(uint64_t)w * pl.n + pos] = pidx | (neg ? 0x80000000u : 0u);
   });
 }
 

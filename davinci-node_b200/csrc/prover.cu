@@ -1,0 +1,381 @@
+// Groth16 proving orchestration on top of the per-curve kernels: device-resident proving keys,
+// the per-proof stream schedule (quotient H + five MSMs + assembly) and the EIP-4844 blob
+// commitment.  Host code only sequences kernels and copies; all arithmetic is on the GPU.
+//
+// Mirrors gnark's `groth16.Prove` data flow behind
+// /root/reference/prover/prover_cpu.go:31-58 and prover_gpu.go:24-164.
+#include "prover.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace b200 {
+
+namespace {
+
+struct DeviceScope {
+  int prev = 0;
+  explicit DeviceScope(int dev) {
+    B200_CUDA(cudaGetDevice(&prev));
+    if (prev != dev) B200_CUDA(cudaSetDevice(dev));
+  }
+  ~DeviceScope() { cudaSetDevice(prev); }
+};
+
+int ilog2_exact(uint64_t n) {
+  int l = 0;
+  while ((1ull << l) < n) l++;
+  if ((1ull << l) != n) throw std::runtime_error("domain size must be a power of two");
+  return l;
+}
+
+void upload(DevBuf& buf, const void* src, size_t bytes, cudaStream_t s) {
+  void* p = buf.get(bytes ? bytes : 16);
+  if (bytes) B200_CUDA(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, s));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ PkInstance
+PkInstance::PkInstance(int dev) : device(dev) {
+  DeviceScope ds(dev);
+  for (auto& s : st) B200_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  for (auto& e : ev) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+
+PkInstance::~PkInstance() {
+  cudaSetDevice(device);
+  for (auto& s : st)
+    if (s) cudaStreamDestroy(s);
+  for (auto& e : ev)
+    if (e) cudaEventDestroy(e);
+}
+
+// ------------------------------------------------------------------------------------ registration
+std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, const std::vector<int>& devices) {
+  CurveBackend* cb = backend_by_id(d.curve);
+  if (!cb) throw std::runtime_error("unsupported curve id " + std::to_string(d.curve));
+  std::unique_ptr<ProvingKeyDev> pk(new ProvingKeyDev());
+  pk->cb = cb;
+  pk->n = d.domain_size;
+  pk->logn = ilog2_exact(d.domain_size);
+  pk->m = d.nb_wires;
+  pk->nb_public = d.nb_public;
+  if (pk->nb_public > pk->m) throw std::runtime_error("nb_public > nb_wires");
+  if (d.infinity_a.len != pk->m || d.infinity_b.len != pk->m)
+    throw std::runtime_error("infinity_a / infinity_b must have nb_wires entries");
+  if (!d.generator || !d.coset_gen || !d.g1_alpha || !d.g1_beta || !d.g1_delta || !d.g2_beta || !d.g2_delta)
+    throw std::runtime_error("null proving-key element");
+
+  const size_t g1b = cb->affine_bytes(1), g2b = cb->affine_bytes(2), frb = cb->fr_bytes();
+  const uint8_t* infA = (const uint8_t*)d.infinity_a.ptr;
+  const uint8_t* infB = (const uint8_t*)d.infinity_b.ptr;
+
+  // ---- index maps over the extended wire vector  W_ext = [w_0 .. w_{m-1}, r, s, 1, -rs]
+  const uint32_t SKIP = 0xffffffffu;
+  std::vector<uint32_t> mapA(pk->m + 4), mapB(pk->m + 4), mapK(pk->m - pk->nb_public + 4);
+  uint64_t ia = 0, ib = 0;
+  for (uint64_t i = 0; i < pk->m; i++) {
+    mapA[i] = infA[i] ? SKIP : (uint32_t)ia++;
+    mapB[i] = infB[i] ? SKIP : (uint32_t)ib++;
+  }
+  if (ia != d.g1_A.len) throw std::runtime_error("len(G1.A) != nb_wires - NbInfinityA");
+  if (ib != d.g1_B.len || ib != d.g2_B.len) throw std::runtime_error("len(G1.B / G2.B) != nb_wires - NbInfinityB");
+  pk->nA = ia;
+  pk->nB = ib;
+  // tail slots: r, s, 1, -rs
+  mapA[pk->m + 0] = (uint32_t)ia;       // r * delta
+  mapA[pk->m + 1] = SKIP;
+  mapA[pk->m + 2] = (uint32_t)ia + 1;   // 1 * alpha
+  mapA[pk->m + 3] = SKIP;
+  mapB[pk->m + 0] = SKIP;
+  mapB[pk->m + 1] = (uint32_t)ib;       // s * delta
+  mapB[pk->m + 2] = (uint32_t)ib + 1;   // 1 * beta
+  mapB[pk->m + 3] = SKIP;
+  const uint32_t* skip = (const uint32_t*)d.krs_skip.ptr;
+  uint64_t nskip = d.krs_skip.len, si = 0, ik = 0;
+  const uint64_t npriv = pk->m - pk->nb_public;
+  for (uint64_t j = 0; j < npriv; j++) {
+    uint64_t wire = pk->nb_public + j;
+    while (si < nskip && skip[si] < wire) si++;
+    if (si < nskip && skip[si] == wire) mapK[j] = SKIP;
+    else mapK[j] = (uint32_t)ik++;
+  }
+  if (ik != d.g1_K.len) throw std::runtime_error("len(G1.K) != private wires - skipped wires");
+  pk->nK = ik;
+  mapK[npriv + 0] = SKIP;
+  mapK[npriv + 1] = SKIP;
+  mapK[npriv + 2] = SKIP;
+  mapK[npriv + 3] = (uint32_t)ik;       // (-rs) * delta
+  pk->nZ = d.g1_Z.len;
+  if (pk->nZ > pk->n) throw std::runtime_error("len(G1.Z) > domain size");
+
+  // ---- commitment keys: concatenated sigma bases, per-commitment bases
+  pk->commit_n.resize(d.nb_commitments);
+  uint64_t total_sigma = 0;
+  for (uint32_t i = 0; i < d.nb_commitments; i++) {
+    if (d.commit_basis[i].len != d.commit_basis_exp_sigma[i].len)
+      throw std::runtime_error("commitment key basis / basisExpSigma length mismatch");
+    pk->commit_n[i] = d.commit_basis[i].len;
+    total_sigma += pk->commit_n[i];
+  }
+  pk->total_commit = total_sigma;
+
+  for (int dev : devices) {
+    DeviceScope ds(dev);
+    std::unique_ptr<PkInstance> in(new PkInstance(dev));
+    cudaStream_t s = in->st[0];
+    auto put_ext = [&](DevBuf& buf, const b200_slice& sl, size_t pb, const void* e0, const void* e1) {
+      uint8_t* p = (uint8_t*)buf.get((sl.len + 2) * pb);
+      if (sl.len) B200_CUDA(cudaMemcpyAsync(p, sl.ptr, sl.len * pb, cudaMemcpyHostToDevice, s));
+      B200_CUDA(cudaMemcpyAsync(p + sl.len * pb, e0, pb, cudaMemcpyHostToDevice, s));
+      if (e1) B200_CUDA(cudaMemcpyAsync(p + (sl.len + 1) * pb, e1, pb, cudaMemcpyHostToDevice, s));
+    };
+    put_ext(in->A, d.g1_A, g1b, d.g1_delta, d.g1_alpha);
+    put_ext(in->B1, d.g1_B, g1b, d.g1_delta, d.g1_beta);
+    put_ext(in->B2, d.g2_B, g2b, d.g2_delta, d.g2_beta);
+    put_ext(in->K, d.g1_K, g1b, d.g1_delta, nullptr);
+    upload(in->Z, d.g1_Z.ptr, d.g1_Z.len * g1b, s);
+    upload(in->mapA, mapA.data(), mapA.size() * 4, s);
+    upload(in->mapB, mapB.data(), mapB.size() * 4, s);
+    upload(in->mapK, mapK.data(), mapK.size() * 4, s);
+    in->basis.resize(d.nb_commitments);
+    uint8_t* sg = (uint8_t*)in->sigma_all.get(std::max<uint64_t>(total_sigma, 1) * g1b);
+    uint64_t off = 0;
+    for (uint32_t i = 0; i < d.nb_commitments; i++) {
+      in->basis[i].reset(new DevBuf());
+      upload(*in->basis[i], d.commit_basis[i].ptr, pk->commit_n[i] * g1b, s);
+      if (pk->commit_n[i])
+        B200_CUDA(cudaMemcpyAsync(sg + off * g1b, d.commit_basis_exp_sigma[i].ptr, pk->commit_n[i] * g1b,
+                                  cudaMemcpyHostToDevice, s));
+      off += pk->commit_n[i];
+    }
+    // ---- domain tables
+    uint8_t* gens = (uint8_t*)in->gens.get(2 * frb);
+    B200_CUDA(cudaMemcpyAsync(gens, d.generator, frb, cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaMemcpyAsync(gens + frb, d.coset_gen, frb, cudaMemcpyHostToDevice, s));
+    cb->domain_init(in->dom, pk->logn, gens, gens + frb, s);
+    // ---- per-proof workspace
+    in->W.get((pk->m + 4) * frb);
+    in->a.get(pk->n * frb);
+    in->b.get(pk->n * frb);
+    in->c.get(pk->n * frb);
+    in->rs.get(2 * frb);
+    in->cvals.get(std::max<uint64_t>(total_sigma, 1) * frb);
+    in->chal.get(frb);
+    in->msm_out.get(6 * cb->xyzz_bytes(2));
+    in->tmp.get(2 * cb->xyzz_bytes(1));
+    in->out_aff.get(3 * g1b + g2b);
+    B200_CUDA(cudaStreamSynchronize(s));
+    pk->inst.push_back(std::move(in));
+  }
+  return pk;
+}
+
+PkInstance& ProvingKeyDev::pick(int device) {
+  if (device >= 0) {
+    for (auto& in : inst)
+      if (in->device == device) return *in;
+    throw std::runtime_error("proving key is not resident on device " + std::to_string(device));
+  }
+  uint32_t k = rr.fetch_add(1) % (uint32_t)inst.size();
+  return *inst[k];
+}
+
+// ------------------------------------------------------------------------------------ prove
+void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, int device, bool inputs_on_device) {
+  PkInstance& I = pick(device);
+  std::lock_guard<std::mutex> lk(I.mu);
+  DeviceScope ds(I.device);
+  const size_t frb = cb->fr_bytes(), g1b = cb->affine_bytes(1), g2b = cb->affine_bytes(2);
+  const size_t x1 = cb->xyzz_bytes(1), x2 = cb->xyzz_bytes(2);
+  if (in.wires.len != m) throw std::runtime_error("wires: expected nb_wires elements");
+  if (in.a.len > n || in.b.len != in.a.len || in.c.len != in.a.len)
+    throw std::runtime_error("a/b/c: need equal lengths <= domain size");
+  if (in.nb_commitments != commit_n.size()) throw std::runtime_error("nb_commitments mismatch with proving key");
+  if (!in.r || !in.s) throw std::runtime_error("r / s missing");
+  const cudaMemcpyKind kind = inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  cudaStream_t s0 = I.st[0], s1 = I.st[1], s2 = I.st[2];
+  uint8_t* W = (uint8_t*)I.W.p;
+  uint8_t* a = (uint8_t*)I.a.p;
+  uint8_t* b = (uint8_t*)I.b.p;
+  uint8_t* c = (uint8_t*)I.c.p;
+
+  // ---- inputs (s0): wire vector first so the A / B MSMs can start while a, b, c are still arriving
+  B200_CUDA(cudaMemcpyAsync(W, in.wires.ptr, m * frb, kind, s0));
+  uint8_t* rs_in = (uint8_t*)I.rs.p;
+  B200_CUDA(cudaMemcpyAsync(rs_in, in.r, frb, kind, s0));
+  B200_CUDA(cudaMemcpyAsync(rs_in + frb, in.s, frb, kind, s0));
+  cb->prep_rs(rs_in, rs_in + frb, W + m * frb, s0);
+  B200_CUDA(cudaEventRecord(I.ev[0], s0));
+
+  uint8_t* mo = (uint8_t*)I.msm_out.p;   // [ar, bs1, k, z, pok] G1 then bs2 G2
+  uint8_t *o_ar = mo, *o_bs1 = mo + x1, *o_k = mo + 2 * x1, *o_z = mo + 3 * x1, *o_pok = mo + 4 * x1,
+          *o_bs2 = mo + 5 * x1;
+
+  // ---- s1: Ar, Bs1   s2: Bs (G2)
+  B200_CUDA(cudaStreamWaitEvent(s1, I.ev[0], 0));
+  cb->msm(1, I.A.p, W, m + 4, o_ar, I.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapA.p);
+  cb->msm(1, I.B1.p, W, m + 4, o_bs1, I.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapB.p);
+  B200_CUDA(cudaEventRecord(I.ev[1], s1));
+  B200_CUDA(cudaStreamWaitEvent(s2, I.ev[0], 0));
+  cb->msm(2, I.B2.p, W, m + 4, o_bs2, I.ws[2], s2, 0, nullptr, (const uint32_t*)I.mapB.p);
+  B200_CUDA(cudaEventRecord(I.ev[2], s2));
+
+  // ---- s0: quotient, Z and K MSMs, proof of knowledge
+  const uint64_t nc = in.a.len;
+  if (nc < n) {
+    B200_CUDA(cudaMemsetAsync(a + nc * frb, 0, (n - nc) * frb, s0));
+    B200_CUDA(cudaMemsetAsync(b + nc * frb, 0, (n - nc) * frb, s0));
+    B200_CUDA(cudaMemsetAsync(c + nc * frb, 0, (n - nc) * frb, s0));
+  }
+  if (nc) {
+    B200_CUDA(cudaMemcpyAsync(a, in.a.ptr, nc * frb, kind, s0));
+    B200_CUDA(cudaMemcpyAsync(b, in.b.ptr, nc * frb, kind, s0));
+    B200_CUDA(cudaMemcpyAsync(c, in.c.ptr, nc * frb, kind, s0));
+  }
+  cb->compute_h(I.dom, a, b, c, s0);
+  cb->msm(1, I.Z.p, a, nZ, o_z, I.ws[0], s0, 0, nullptr, nullptr);
+  cb->msm(1, I.K.p, W + nb_public * frb, m - nb_public + 4, o_k, I.ws[0], s0, 0, nullptr,
+          (const uint32_t*)I.mapK.p);
+  bool have_pok = total_commit > 0 || !commit_n.empty();
+  if (have_pok) {
+    uint8_t* cv = (uint8_t*)I.cvals.p;
+    uint64_t off = 0;
+    for (size_t i = 0; i < commit_n.size(); i++) {
+      if (in.priv_committed[i].len != commit_n[i])
+        throw std::runtime_error("private committed values: length mismatch with commitment key");
+      if (commit_n[i]) B200_CUDA(cudaMemcpyAsync(cv + off * frb, in.priv_committed[i].ptr, commit_n[i] * frb, kind, s0));
+      if (i >= 1) {
+        if (!in.fold_challenge) throw std::runtime_error("fold_challenge required with more than one commitment");
+        if (i == 1) B200_CUDA(cudaMemcpyAsync(I.chal.p, in.fold_challenge, frb, kind, s0));
+        // segment i is scaled by challenge^i : scale every later segment once per step
+      }
+      off += commit_n[i];
+    }
+    // scale segments [i..] by the challenge, for i = 1 .. k-1  => segment j picks up challenge^j
+    off = 0;
+    for (size_t i = 0; i < commit_n.size(); i++) {
+      if (i >= 1) cb->scale_vec(cv + off * frb, I.chal.p, total_commit - off, s0);
+      off += commit_n[i];
+    }
+    cb->msm(1, I.sigma_all.p, cv, total_commit, o_pok, I.ws[0], s0, 0, nullptr, nullptr);
+  }
+  B200_CUDA(cudaStreamWaitEvent(s0, I.ev[1], 0));
+  B200_CUDA(cudaStreamWaitEvent(s0, I.ev[2], 0));
+
+  uint8_t* oa = (uint8_t*)I.out_aff.p;   // ar, krs, pok (G1), bs (G2)
+  AssembleArgs aa{};
+  aa.ar_msm = o_ar;
+  aa.bs1_msm = o_bs1;
+  aa.bs2_msm = o_bs2;
+  aa.k_msm = o_k;
+  aa.z_msm = o_z;
+  aa.pok_msm = have_pok ? o_pok : nullptr;
+  aa.rs = W + m * frb;
+  aa.tmp = I.tmp.p;
+  aa.out_ar = oa;
+  aa.out_krs = oa + g1b;
+  aa.out_pok = oa + 2 * g1b;
+  aa.out_bs = oa + 3 * g1b;
+  cb->assemble(aa, s0);
+  const cudaMemcpyKind back = inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  B200_CUDA(cudaMemcpyAsync(out.ar, oa, g1b, back, s0));
+  B200_CUDA(cudaMemcpyAsync(out.krs, oa + g1b, g1b, back, s0));
+  if (have_pok && out.pok) B200_CUDA(cudaMemcpyAsync(out.pok, oa + 2 * g1b, g1b, back, s0));
+  B200_CUDA(cudaMemcpyAsync(out.bs, oa + 3 * g1b, g2b, back, s0));
+  B200_CUDA(cudaStreamSynchronize(s0));
+  (void)x2;
+}
+
+// commitment i = sum_j values[j] * Basis_i[j]   (called from the solver hint, synchronous)
+void ProvingKeyDev::commit(uint32_t i, const b200_slice& values, void* out_affine, int device) {
+  if (i >= commit_n.size()) throw std::runtime_error("commitment index out of range");
+  if (values.len != commit_n[i]) throw std::runtime_error("commit: values length mismatch with Basis");
+  PkInstance& I = pick(device);
+  std::lock_guard<std::mutex> lk(I.mu);
+  DeviceScope ds(I.device);
+  const size_t frb = cb->fr_bytes(), g1b = cb->affine_bytes(1);
+  cudaStream_t s0 = I.st[0];
+  uint8_t* cv = (uint8_t*)I.cvals.p;
+  if (values.len) B200_CUDA(cudaMemcpyAsync(cv, values.ptr, values.len * frb, cudaMemcpyHostToDevice, s0));
+  uint8_t* mo = (uint8_t*)I.msm_out.p;
+  cb->msm(1, I.basis[i]->p, cv, values.len, mo, I.ws[0], s0, 0, nullptr, nullptr);
+  cb->to_affine(1, mo, I.out_aff.p, 1, s0);
+  B200_CUDA(cudaMemcpyAsync(out_affine, I.out_aff.p, g1b, cudaMemcpyDeviceToHost, s0));
+  B200_CUDA(cudaStreamSynchronize(s0));
+}
+
+// ------------------------------------------------------------------------------------ KZG
+std::unique_ptr<KzgSrsDev> KzgSrsDev::create(const uint8_t* g1_lagrange_compressed, uint32_t npoints,
+                                             const std::vector<int>& devices) {
+  CurveBackend* cb = backend_by_id(3);
+  if (npoints == 0 || (npoints & (npoints - 1))) throw std::runtime_error("SRS size must be a power of two");
+  std::unique_ptr<KzgSrsDev> srs(new KzgSrsDev());
+  srs->cb = cb;
+  srs->npoints = npoints;
+  int logn = ilog2_exact(npoints);
+  std::vector<uint32_t> brp(npoints);
+  for (uint32_t i = 0; i < npoints; i++) {
+    uint32_t r = 0;
+    for (int b = 0; b < logn; b++) r |= ((i >> b) & 1u) << (logn - 1 - b);
+    brp[i] = r;
+  }
+  for (int dev : devices) {
+    DeviceScope ds(dev);
+    std::unique_ptr<KzgSrsDev::Inst> in(new KzgSrsDev::Inst());
+    in->device = dev;
+    B200_CUDA(cudaStreamCreateWithFlags(&in->st, cudaStreamNonBlocking));
+    const size_t g1b = cb->affine_bytes(1);
+    DevBuf raw;
+    upload(raw, g1_lagrange_compressed, (size_t)npoints * 48, in->st);
+    in->points.get((size_t)npoints * g1b);
+    uint32_t* err = (uint32_t*)in->err.get(4);
+    B200_CUDA(cudaMemsetAsync(err, 0, 4, in->st));
+    cb->g1_decompress(raw.p, in->points.p, npoints, err, in->st);
+    upload(in->brp, brp.data(), (size_t)npoints * 4, in->st);
+    in->blob.get((size_t)npoints * 32);
+    in->scalars.get((size_t)npoints * cb->fr_bytes());
+    in->out.get(cb->xyzz_bytes(1) + g1b + 64);
+    uint32_t herr = 0;
+    B200_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, in->st));
+    B200_CUDA(cudaStreamSynchronize(in->st));
+    if (herr) throw std::runtime_error("SRS contains an invalid compressed G1 point (flags " + std::to_string(herr) + ")");
+    srs->inst.push_back(std::move(in));
+  }
+  return srs;
+}
+
+KzgSrsDev::Inst::~Inst() {
+  cudaSetDevice(device);
+  if (st) cudaStreamDestroy(st);
+}
+
+void KzgSrsDev::blob_commit(const uint8_t* blob, uint8_t* commitment48, int device) {
+  Inst* I = nullptr;
+  if (device >= 0) {
+    for (auto& in : inst)
+      if (in->device == device) I = in.get();
+    if (!I) throw std::runtime_error("SRS is not resident on device " + std::to_string(device));
+  } else {
+    I = inst[rr.fetch_add(1) % inst.size()].get();
+  }
+  std::lock_guard<std::mutex> lk(I->mu);
+  DeviceScope ds(I->device);
+  const size_t g1b = cb->affine_bytes(1), x1 = cb->xyzz_bytes(1);
+  uint32_t* err = (uint32_t*)I->err.p;
+  B200_CUDA(cudaMemsetAsync(err, 0, 4, I->st));
+  B200_CUDA(cudaMemcpyAsync(I->blob.p, blob, (size_t)npoints * 32, cudaMemcpyHostToDevice, I->st));
+  cb->blob_to_scalars(I->blob.p, I->scalars.p, npoints, err, I->st);
+  uint8_t* o = (uint8_t*)I->out.p;
+  cb->msm(1, I->points.p, I->scalars.p, npoints, o, I->ws, I->st, 0, nullptr, (const uint32_t*)I->brp.p);
+  cb->to_affine(1, o, o + x1, 1, I->st);
+  cb->g1_compress(o + x1, o + x1 + g1b, 1, I->st);
+  uint32_t herr = 0;
+  B200_CUDA(cudaMemcpyAsync(commitment48, o + x1 + g1b, 48, cudaMemcpyDeviceToHost, I->st));
+  B200_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, I->st));
+  B200_CUDA(cudaStreamSynchronize(I->st));
+  if (herr) throw std::runtime_error("blob contains a non-canonical field element (>= BLS12-381 r)");
+}
+
+}  // namespace b200

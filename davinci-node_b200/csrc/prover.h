@@ -1,0 +1,61 @@
+// Device-resident proving keys / SRS and the proving schedule (see prover.cu).
+#pragma once
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "../../include/b200_groth16.h"
+#include "backend.h"
+
+namespace b200 {
+
+// One copy of a proving key on one GPU, with the workspace for one proof in flight.
+struct PkInstance {
+  int device;
+  std::mutex mu;
+  cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  DevBuf A, B1, B2, K, Z, mapA, mapB, mapK, sigma_all, gens;
+  std::vector<std::unique_ptr<DevBuf>> basis;
+  NttDomain dom;
+  // per-proof workspace
+  DevBuf W, a, b, c, rs, cvals, chal, msm_out, tmp, out_aff;
+  MsmWorkspace ws[3];
+  explicit PkInstance(int dev);
+  ~PkInstance();
+};
+
+struct ProvingKeyDev {
+  CurveBackend* cb = nullptr;
+  uint64_t n = 0, m = 0, nb_public = 0, nA = 0, nB = 0, nK = 0, nZ = 0, total_commit = 0;
+  int logn = 0;
+  std::vector<uint64_t> commit_n;
+  std::vector<std::unique_ptr<PkInstance>> inst;
+  std::atomic<uint32_t> rr{0};
+
+  static std::unique_ptr<ProvingKeyDev> create(const b200_pk_desc& d, const std::vector<int>& devices);
+  PkInstance& pick(int device);
+  void prove(const b200_prove_in& in, const b200_proof_out& out, int device, bool inputs_on_device);
+  void commit(uint32_t i, const b200_slice& values, void* out_affine, int device);
+};
+
+struct KzgSrsDev {
+  struct Inst {
+    int device = 0;
+    std::mutex mu;
+    cudaStream_t st = nullptr;
+    DevBuf points, brp, blob, scalars, out, err;
+    MsmWorkspace ws;
+    ~Inst();
+  };
+  CurveBackend* cb = nullptr;
+  uint32_t npoints = 0;
+  std::vector<std::unique_ptr<Inst>> inst;
+  std::atomic<uint32_t> rr{0};
+  static std::unique_ptr<KzgSrsDev> create(const uint8_t* g1_lagrange_compressed, uint32_t npoints,
+                                           const std::vector<int>& devices);
+  void blob_commit(const uint8_t* blob, uint8_t* commitment48, int device);
+};
+
+}  // namespace b200

@@ -65,6 +65,91 @@ B200_API int b200_to_affine_dev(int curve, int group, const void* d_xyzz, void* 
  * [3]=task size, [4]=group size */
 B200_API int b200_msm_plan(int curve, uint64_t n, int window_bits, uint32_t out[5]);
 
+/* ---- NTT (gnark-crypto fft.Domain semantics) --------------------------------------------------
+ * Replaces fft.Domain.FFT / FFTInverse (gnark-crypto) and icicle's Ntt.
+ * A domain holds the twiddle / coset tables resident in HBM for one (curve, size) on the current
+ * device.  generator / coset_gen: fr elements in Montgomery form (pk.Domain.Generator,
+ * pk.Domain.FrMultiplicativeGen), host pointers. */
+B200_API int b200_domain_create(int curve, uint64_t size, const void* generator, const void* coset_gen,
+                                uint64_t* domain_out);
+B200_API int b200_domain_release(uint64_t domain);
+/* in-place transform of `size` fr elements on the device.
+ * inverse: 0 FFT, 1 FFTInverse (scaled by 1/n) ; decimation: 0 DIF (natural in, bit-reversed out),
+ * 1 DIT (bit-reversed in, natural out) ; coset: 0/1 as gnark's fft.OnCoset() */
+B200_API int b200_ntt_dev(uint64_t domain, void* d_data, int inverse, int decimation, int coset, void* cuda_stream);
+/* quotient polynomial: d_a <- coefficients of h = (a*b - c)/(X^n - 1) in bit-reversed order, exactly
+ * gnark's computeH (7 transforms + fused pointwise work).  d_a, d_b, d_c: `size` fr each (zero padded),
+ * all three are overwritten. */
+B200_API int b200_compute_h_dev(uint64_t domain, void* d_a, void* d_b, void* d_c, void* cuda_stream);
+
+/* ---- Groth16 proving key / prove ---------------------------------------------------------------
+ * b200_slice: (pointer, element count) view of a Go slice; elements in gnark-crypto memory layout. */
+typedef struct {
+  const void* ptr;
+  uint64_t len;
+} b200_slice;
+
+/* Everything groth16.Prove reads from *groth16_<curve>.ProvingKey plus the R1CS metadata the
+ * prover needs (gnark `ProvingKey` exported fields).  Copied to every selected GPU. */
+typedef struct {
+  int curve;
+  uint64_t domain_size;           /* pk.Domain.Cardinality */
+  const void* generator;          /* pk.Domain.Generator            (fr) */
+  const void* coset_gen;          /* pk.Domain.FrMultiplicativeGen  (fr) */
+  const void* g1_alpha;           /* pk.G1.Alpha, Beta, Delta       (G1Affine) */
+  const void* g1_beta;
+  const void* g1_delta;
+  b200_slice g1_A, g1_B, g1_Z, g1_K;   /* pk.G1.A / B / Z / K */
+  const void* g2_beta;            /* pk.G2.Beta, Delta              (G2Affine) */
+  const void* g2_delta;
+  b200_slice g2_B;                /* pk.G2.B */
+  b200_slice infinity_a;          /* pk.InfinityA, pk.InfinityB: []bool, one byte per wire */
+  b200_slice infinity_b;
+  uint64_t nb_wires;              /* len(InfinityA) = internal + secret + public variables */
+  uint64_t nb_public;             /* r1cs.GetNbPublicVariables() (includes the constant-one wire) */
+  b200_slice krs_skip;            /* ascending uint32 wire ids left out of the K MSM: every
+                                     commitmentInfo[i].PrivateCommitted wire and CommitmentIndex wire */
+  uint32_t nb_commitments;        /* len(pk.CommitmentKeys) */
+  const b200_slice* commit_basis;            /* pk.CommitmentKeys[i].Basis */
+  const b200_slice* commit_basis_exp_sigma;  /* pk.CommitmentKeys[i].BasisExpSigma */
+} b200_pk_desc;
+
+typedef struct {
+  b200_slice wires;               /* solution.W : nb_wires fr */
+  b200_slice a, b, c;             /* solution.A / B / C : nbConstraints fr each */
+  const void* r;                  /* prover randomness, fr Montgomery (pinned by tests, crypto/rand otherwise) */
+  const void* s;
+  uint32_t nb_commitments;
+  const b200_slice* priv_committed;   /* privateCommittedValues[i] */
+  const void* fold_challenge;     /* fr; only read when nb_commitments > 1 */
+} b200_prove_in;
+
+typedef struct {
+  void* ar;    /* proof.Ar   G1Affine */
+  void* bs;    /* proof.Bs   G2Affine */
+  void* krs;   /* proof.Krs  G1Affine */
+  void* pok;   /* proof.CommitmentPok G1Affine (untouched when the circuit has no commitment) */
+} b200_proof_out;
+
+/* Upload a proving key (replaces icicle's device-side pk setup behind prover/prover_gpu.go:24-61). */
+B200_API int b200_pk_register(const b200_pk_desc* desc, uint64_t* handle_out);
+B200_API int b200_pk_release(uint64_t handle);
+/* Pedersen commitment i over Basis: called from the BSB22 solver hint. */
+B200_API int b200_commit(uint64_t handle, uint32_t i, b200_slice values, void* out_g1_affine, int device);
+/* The proof: replaces groth16.Prove's computeH + MultiExp section (prover/prover_cpu.go:37,57;
+ * gpugroth16.Prove at prover/prover_gpu.go:33-56).  device = -1 picks a GPU round-robin. */
+B200_API int b200_prove(uint64_t handle, const b200_prove_in* in, const b200_proof_out* out, int device);
+/* same, every pointer in `in` / `out` is a device pointer on the key's device (resident pipeline) */
+B200_API int b200_prove_dev(uint64_t handle, const b200_prove_in* in, const b200_proof_out* out, int device);
+
+/* ---- EIP-4844 blob commitment (BLS12-381) -----------------------------------------------------
+ * Replaces gethkzg.BlobToCommitment (types/blobs.go:90-96). */
+/* g1_lagrange: npoints x 48-byte compressed points in the order of config/kzg_trusted_setup.txt */
+B200_API int b200_kzg_srs_register(const uint8_t* g1_lagrange, uint32_t npoints, uint64_t* handle_out);
+B200_API int b200_kzg_srs_release(uint64_t handle);
+B200_API int b200_blob_commit(uint64_t srs, const uint8_t* blob /* npoints*32 bytes */, uint8_t commitment_out[48],
+                              int device);
+
 /* ---- debug / parity entry points (device pointers; element-wise over n items) ---------------
  * field: 0 = Fp, 1 = Fr, 2 = Fp2 ; op: 0 add, 1 sub, 2 mul, 3 sqr, 4 from_mont, 5 to_mont, 6 inv, 7 neg */
 B200_API int b200_dbg_field_op_dev(int curve, int field, int op, const void* d_a, const void* d_b, void* d_out, uint64_t n,

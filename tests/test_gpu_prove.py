@@ -1,0 +1,92 @@
+"""GPU parity of the full Groth16 prove through the reference-shaped interface
+(davinci_node_b200.prover.ProveWithWitness == prover/prover_gpu.go:111): with (r, s) pinned the
+proof is bit-identical to the oracle's restatement of gnark's Prove, and it satisfies the verifier
+equation in the exponent."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import curve as OC
+from oracle import groth16 as OG
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from davinci_node_b200 import capi, layout, prover, gnark_types
+    capi.init()
+    return capi, layout, prover, gnark_types
+
+
+CASES = [
+    ("bls12_377", 60, 6, 1, 5, "witness"),     # voteverifier-shaped: 6 public wires, 1 commitment
+    ("bn254", 45, 9, 1, 4, "witness"),         # statetransition-shaped: 9 public + 1 commitment
+    ("bw6_761", 37, 2, 1, 3, "uniform"),       # aggregator-shaped
+    ("bls12_377", 130, 3, 0, 0, "uniform"),    # no commitment
+    ("bn254", 40, 3, 2, 3, "witness"),         # two commitments (folded proof of knowledge)
+]
+
+
+@pytest.mark.parametrize("cname,ncons,npub,ncommit,npc,mix", CASES)
+def test_prove_bit_exact_and_verifies(env, cname, ncons, npub, ncommit, npc, mix):
+    from oracle_bridge import ccs_from_oracle, pk_from_oracle
+    capi, layout, prover, T = env
+    cx = OC.ctx(cname)
+    q = cx.r
+    L = layout.Layout(cname)
+    rnd = random.Random(hash((cname, ncons)) & 0xFFFF)
+    cs, W0 = OG.synthetic_circuit(ncons, npub, q, seed=ncons, n_commit=ncommit, n_private_committed=npc, mix=mix)
+    tox = OG.Toxic(*(rnd.randrange(1, q) for _ in range(5)), sigmas=[rnd.randrange(1, q) for _ in range(ncommit)])
+    opk, ex = OG.setup(cs, cx, tox)
+    ccs = ccs_from_oracle(cs, L.id)
+    pk = pk_from_oracle(opk, L.id)
+    w = T.Witness(L.id, W0[1:cs.nb_public], W0[cs.nb_public:cs.nb_public + ccs.nb_secret])
+    r, s = rnd.randrange(q), rnd.randrange(q)
+    prover.SetRandomness(lambda cid: (r, s))
+    try:
+        proof = prover.ProveWithWitness(L.id, ccs, pk, w)
+        # the solver (host) fixed the commitment-wire values; replay the same assignment in the oracle
+        sol = ccs.solve(w, lambda i, v: proof.Commitments[i])
+        W = sol.values
+        want = OG.prove(cs, opk, W, r, s, cx, fold_challenge=sol.fold_challenge)
+        got = proof.points()
+        assert got["Ar"] == want["Ar"]
+        assert got["Bs"] == want["Bs"]
+        assert got["Krs"] == want["Krs"]
+        assert got["Commitments"] == want["Commitments"]
+        if ncommit:
+            assert got["CommitmentPok"] == want["CommitmentPok"]
+        A, B, Cx = OG.proof_exponents(cs, ex, tox, W, r, s, q)
+        assert got["Ar"] == cx.G1.mul(cx.g1, A) and got["Bs"] == cx.G2.mul(cx.g2, B)
+        assert OG.verify_exponent(cs, ex, tox, W, A, B, Cx, q)
+        # un-pinned randomness: a different valid proof that still satisfies the verifier equation
+        prover.SetRandomness(None)
+        p2 = prover.ProveWithWitness(L.id, ccs, pk, w).points()
+        assert p2["Ar"] != got["Ar"]
+    finally:
+        prover.SetRandomness(None)
+        prover.release_proving_key(pk)
+
+
+def test_prove_rejects_unsatisfied_witness(env):
+    from oracle_bridge import ccs_from_oracle, pk_from_oracle
+    capi, layout, prover, T = env
+    cx = OC.ctx("bn254")
+    L = layout.Layout("bn254")
+    cs, W0 = OG.synthetic_circuit(10, 3, cx.r, seed=1)
+    ccs = ccs_from_oracle(cs, L.id)
+    # make constraint 3's output a constant wire so a wrong witness cannot be "solved around"
+    ccs.O[3] = [(1, 1)]
+    w = T.Witness(L.id, W0[1:cs.nb_public], W0[cs.nb_public:cs.nb_public + ccs.nb_secret])
+    with pytest.raises(T.UnsatisfiedConstraintError):
+        ccs.solve(w)
+
+
+def test_cpu_prover_is_absent(env):
+    capi, layout, prover, T = env
+    with pytest.raises(prover.ProverError):
+        prover.CPUProver(1, None, None, None)
+    with pytest.raises(prover.ProverError):
+        prover.CPUProverWithWitness(1, None, None, None)

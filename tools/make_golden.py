@@ -1,0 +1,57 @@
+#!/usr/bin/env python3
+"""Builds the committed fixtures under tests/golden/ from the reference's own data files.
+Run in the build container only (reads /root/reference); the GPU box uses the committed outputs.
+
+  kzg_g1_lagrange.bin   4096 x 48-byte compressed G1 Lagrange points, file order
+                        (/root/reference/config/kzg_trusted_setup.txt lines 3..4098)
+  kzg_g1_monomial_64.bin first 64 monomial-basis G1 points (lines 4164..) for the cross-check
+  kzg_kat.json          known-answer commitments computed by the oracle (oracle/kzg.py) for the
+                        reference's deterministic test blobs (crypto/blobs/testdata.go:101-132) and
+                        the first 128 KiB sample blob (crypto/blobs/testdata/blobdata1.txt)
+"""
+import hashlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import kzg  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    lines = open(os.path.join(REF, "config", "kzg_trusted_setup.txt")).read().split()
+    n1, n2 = int(lines[0]), int(lines[1])
+    assert (n1, n2) == (4096, 65)
+    lag_hex = lines[2:2 + n1]
+    mono_hex = lines[2 + n1 + n2:2 + n1 + n2 + n1]
+    lag_bytes = b"".join(bytes.fromhex(h) for h in lag_hex)
+    open(os.path.join(OUT, "kzg_g1_lagrange.bin"), "wb").write(lag_bytes)
+    open(os.path.join(OUT, "kzg_g1_monomial_64.bin"), "wb").write(b"".join(bytes.fromhex(h) for h in mono_hex[:64]))
+    lag = [kzg.g1_decompress(bytes.fromhex(h)) for h in lag_hex]
+
+    kat = {"srs_sha256": hashlib.sha256(lag_bytes).hexdigest(), "cases": []}
+
+    def seed_blob(seed):
+        b = bytearray(4096 * 32)
+        for i in range(50):
+            b[i * 32:(i + 1) * 32] = (seed + i).to_bytes(32, "big")
+        return bytes(b)
+
+    ones = b"".join((1).to_bytes(32, "big") for _ in range(4096))
+    sample = bytes.fromhex(open(os.path.join(REF, "crypto", "blobs", "testdata", "blobdata1.txt")).read().strip())
+    open(os.path.join(OUT, "blobdata1.bin"), "wb").write(sample)
+    for name, blob in [("seed1", seed_blob(1)), ("seed2", seed_blob(2)), ("all_ones", ones), ("zero", bytes(4096 * 32)),
+                       ("blobdata1", sample)]:
+        c = kzg.blob_to_commitment(blob, lag)
+        kat["cases"].append({"name": name, "blob_sha256": hashlib.sha256(blob).hexdigest(), "commitment": c.hex()})
+        print(name, c.hex())
+    json.dump(kat, open(os.path.join(OUT, "kzg_kat.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
