@@ -197,22 +197,23 @@ struct EC {
     r = acc;
   }
 
-  // affine normalisation: x = X/ZZ, y = Y/ZZZ ; infinity -> (0, 0)
-  static __device__ __noinline__ void to_affine(Aff& r, const Pt& p) {
-    if (is_inf(p)) {
-      F::set_zero(r.x);
-      F::set_zero(r.y);
-      return;
+  // affine normalisation: x = X/ZZ, y = Y/ZZZ ; infinity -> (0, 0).  Inlined (the inversion inside
+  // is the only out-of-line call) and written through a local with a single exit.
+  static __device__ __forceinline__ void to_affine(Aff& r, const Pt& p) {
+    Aff o;
+    F::set_zero(o.x);
+    F::set_zero(o.y);
+    if (!is_inf(p)) {
+      // 1/ZZ and 1/ZZZ from a single inversion of ZZ*ZZZ
+      El t, ti, izz, izzz;
+      F::mul(t, p.zz, p.zzz);
+      F::inv(ti, t);
+      F::mul(izz, ti, p.zzz);
+      F::mul(izzz, ti, p.zz);
+      F::mul(o.x, p.x, izz);
+      F::mul(o.y, p.y, izzz);
     }
-    // 1/ZZ and 1/ZZZ from a single inversion of ZZ*ZZZ
-    El t, ti;
-    F::mul(t, p.zz, p.zzz);
-    F::inv(ti, t);
-    El izz, izzz;
-    F::mul(izz, ti, p.zzz);
-    F::mul(izzz, ti, p.zz);
-    F::mul(r.x, p.x, izz);
-    F::mul(r.y, p.y, izzz);
+    r = o;
   }
 };
 
