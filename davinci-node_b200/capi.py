@@ -63,6 +63,10 @@ _PROTOS = {
     "b200_commit": (_i, [_u64, _u32, Slice, _vp, _i]),
     "b200_prove": (_i, [_u64, C.POINTER(ProveIn), C.POINTER(ProofOut), _i]),
     "b200_prove_dev": (_i, [_u64, C.POINTER(ProveIn), C.POINTER(ProofOut), _i]),
+    "b200_fixed_base_dev": (_i, [_i, _i, _vp, _vp, _u64, _vp, _vp]),
+    "b200_launch_count": (_u64, []),
+    "b200_profile_enable": (_i, [_i]),
+    "b200_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(_u64)]),
     "b200_kzg_srs_register": (_i, [_vp, _u32, C.POINTER(_u64)]),
     "b200_kzg_srs_release": (_i, [_u64]),
     "b200_blob_commit": (_i, [_u64, _vp, _vp, _i]),

@@ -22,6 +22,16 @@ struct CudaError : std::runtime_error {
                               std::to_string(__LINE__) + ")");                                       \
   } while (0)
 
+// ---- instrumentation (off by default): kernel launch counter and CUDA-event kernel timers
+enum ProfTag { PROF_MSM_ACC_G1 = 0, PROF_MSM_ACC_G2 = 1, PROF_NTT_PASS = 2, PROF_MSM_TOTAL_G1 = 3, PROF_MSM_TOTAL_G2 = 4,
+               PROF_TAGS = 5 };
+void prof_count_launches(uint64_t n);
+uint64_t prof_launches();
+bool prof_enabled();
+// returns an opaque token (or -1 when profiling is off); records the start event on `s`
+int prof_begin(int tag, cudaStream_t s);
+void prof_end(int token, cudaStream_t s);
+
 // Growable device scratch buffer (stream-ordered use; never shrinks).
 struct DevBuf {
   void* p = nullptr;
@@ -128,6 +138,9 @@ struct CurveBackend {
                          cudaStream_t s) = 0;
   // --- throughput calibration: `iters` dependent Montgomery multiplications per thread (fp)
   virtual void calib_mul(int field, void* d_inout, uint64_t nthreads, int iters, cudaStream_t s) = 0;
+  // --- fixed-base batch scalar multiplication: out[i] = affine([k_i] base)   (Setup building block)
+  virtual void fixed_base(int group, const void* d_base_affine, const void* d_scalars_mont, uint64_t n,
+                          void* d_out_affine, cudaStream_t s) = 0;
 };
 
 CurveBackend* backend_bn254();

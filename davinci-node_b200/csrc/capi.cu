@@ -3,6 +3,7 @@
 // workspace pooling, error capture.  No arithmetic happens on the CPU.
 #include "../../include/b200_groth16.h"
 
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -13,6 +14,37 @@
 #include "prover.h"
 
 using namespace b200;
+
+// ---------------------------------------------------------------------------------- instrumentation
+namespace b200 {
+namespace {
+std::atomic<uint64_t> g_launch_count{0};
+std::atomic<bool> g_prof_on{false};
+struct ProfRec {
+  int tag;
+  cudaEvent_t e0, e1;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+}  // namespace
+void prof_count_launches(uint64_t n) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+uint64_t prof_launches() { return g_launch_count.load(); }
+bool prof_enabled() { return g_prof_on.load(); }
+int prof_begin(int tag, cudaStream_t s) {
+  if (!g_prof_on.load()) return -1;
+  ProfRec r{tag, nullptr, nullptr};
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+  cudaEventRecord(r.e0, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+void prof_end(int token, cudaStream_t s) {
+  if (token < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if ((size_t)token < g_prof.size()) cudaEventRecord(g_prof[token].e1, s);
+}
+}  // namespace b200
 
 namespace {
 
@@ -350,6 +382,51 @@ int b200_blob_commit(uint64_t h, const uint8_t* blob, uint8_t commitment_out[48]
       srs = it->second;
     }
     srs->blob_commit(blob, commitment_out, device);
+  });
+}
+
+// ---------------------------------------------------------------------------------- setup / instrumentation
+int b200_fixed_base_dev(int curve_id, int group, const void* d_base_affine, const void* d_scalars, uint64_t n,
+                        void* d_out_affine, void* stream) {
+  return guarded([&] {
+    check_group(group);
+    curve(curve_id).fixed_base(group, d_base_affine, d_scalars, n, d_out_affine, (cudaStream_t)stream);
+  });
+}
+
+uint64_t b200_launch_count(void) { return prof_launches(); }
+
+int b200_profile_enable(int on) {
+  return guarded([&] {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) {
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    g_prof_on.store(on != 0);
+  });
+}
+
+// Synchronises the device, then sums elapsed ms and launch counts per tag (see ProfTag) and clears.
+int b200_profile_collect(double ms_out[5], uint64_t count_out[5]) {
+  return guarded([&] {
+    B200_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int t = 0; t < PROF_TAGS; t++) {
+      ms_out[t] = 0;
+      count_out[t] = 0;
+    }
+    for (auto& r : g_prof) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+        ms_out[r.tag] += ms;
+        count_out[r.tag]++;
+      }
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
   });
 }
 

@@ -90,6 +90,24 @@ __global__ void k_to_affine(const XYZZ<F>* in, Affine<F>* out, uint32_t n) {
   out[i] = q;
 }
 
+// out[i] = affine([k_i] base): one thread per scalar (double-and-add, leading zero bits skipped)
+template <class F, class Fr>
+__global__ void __launch_bounds__(64) k_fixed_base(const Affine<F>* base, const typename Fr::El* scalars, uint64_t n,
+                                                    Affine<F>* out) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename Fr::El k;
+  load16(k, scalars + i);
+  Fr::from_mont(k, k);
+  XYZZ<F> b, r;
+  Affine<F> ba = *base;
+  EC<F>::from_affine(b, ba);
+  EC<F>::template mul_scalar<Fr::N>(r, b, k.v);
+  Affine<F> o;
+  EC<F>::to_affine(o, r);
+  store16(out + i, o);
+}
+
 // dependent multiply chain: measures the sustained Montgomery-multiply (IMAD.WIDE) issue rate
 template <class F>
 __global__ void __launch_bounds__(256) k_calib_mul(typename F::El* io, uint64_t n, int iters) {
@@ -162,7 +180,7 @@ __global__ void k_assemble_out(const XYZZ<F1>* ar, const XYZZ<F2>* bs2, const XY
 }
 
 // ------------------------------------------------------------------------------------ MSM driver
-template <class F, class Fr>
+template <class F, class Fr, int GROUP>
 void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d_out, MsmWorkspace& ws,
                 cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map) {
   using Pt = XYZZ<F>;
@@ -192,11 +210,14 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   const auto* sc = reinterpret_cast<const typename Fr::El*>(d_scalars);
   const auto* pts = reinterpret_cast<const Affine<F>*>(d_points);
   const unsigned sblocks = (unsigned)((n + 255) / 256);
+  const int tok_total = prof_begin(GROUP == 2 ? PROF_MSM_TOTAL_G2 : PROF_MSM_TOTAL_G1, s);
   k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, d_index_map);
   k_msm_scan<<<pl.nwin, 1024, 0, s>>>(hist, pl, off, cur);
   k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, d_index_map);
+  const int tok_acc = prof_begin(GROUP == 2 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1, s);
   k_msm_accumulate<F><<<(unsigned)((total_b + 127) / 128), 128, 0, s>>>(pts, sorted, off, cur, pl, buckets, tasks,
                                                                          obuckets, ctr);
+  prof_end(tok_acc, s);
   // oversized buckets (skewed scalar distributions, e.g. the many 1-valued witness wires)
   unsigned ovf_blocks = (unsigned)std::min<uint64_t>((pl.max_ovf + 127) / 128, 148 * 8);
   k_msm_ovf_accumulate<F><<<ovf_blocks, 128, 0, s>>>(pts, sorted, pl, tasks, ctr, partial);
@@ -206,6 +227,8 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   k_msm_bucket_reduce<F><<<(pl.nwin * ngroups + 63) / 64, 64, 0, s>>>(buckets, pl, groups);
   k_msm_window_sum<F><<<pl.nwin, kReduceThreads, red_smem, s>>>(groups, pl, windows);
   k_msm_horner<F><<<1, 32, 0, s>>>(windows, pl, (Pt*)d_out);
+  prof_end(tok_total, s);
+  prof_count_launches(9);
   B200_CUDA(cudaGetLastError());
 }
 
@@ -227,8 +250,8 @@ struct CurveImpl : CurveBackend {
 
   void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out, MsmWorkspace& ws,
            cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map) override {
-    if (group == 1) msm_launch<G1F, Fr>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map);
-    else msm_launch<G2F, Fr>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map);
+    if (group == 1) msm_launch<G1F, Fr, 1>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map);
+    else msm_launch<G2F, Fr, 2>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map);
   }
 
   // ---------------------------------------------------------------- NTT
@@ -267,9 +290,12 @@ struct CurveImpl : CurveBackend {
       unsigned blocks = 1u << (logn - elog);
       size_t smem = sizeof(FrEl) << elog;
       bool first = i == 0, last = i + 1 == passes.size();
+      const int tok = prof_begin(PROF_NTT_PASS, s);
       k_ntt_pass<Fr, DIT><<<blocks, kNttThreads, smem, s>>>(data, tw, ps, first ? pre : none, last ? post : none,
                                                            first ? in_b : nullptr, first ? in_c : nullptr, den);
+      prof_end(tok, s);
     }
+    prof_count_launches(passes.size());
     B200_CUDA(cudaGetLastError());
   }
 
@@ -357,12 +383,14 @@ struct CurveImpl : CurveBackend {
   }
 
   void prep_rs(const void* d_r, const void* d_s, void* d_out4, cudaStream_t s) override {
+    prof_count_launches(1);
     k_prep_rs<Fr><<<1, 1, 0, s>>>((const FrEl*)d_r, (const FrEl*)d_s, (FrEl*)d_out4);
     B200_CUDA(cudaGetLastError());
   }
 
   void assemble(const AssembleArgs& a, cudaStream_t s) override {
     using P1 = XYZZ<G1F>;
+    prof_count_launches(2);
     k_assemble_mul<G1F, Fr><<<2, 1, 0, s>>>((const P1*)a.ar_msm, (const P1*)a.bs1_msm, (const FrEl*)a.rs, (P1*)a.tmp);
     k_assemble_out<G1F, G2F><<<4, 1, 0, s>>>((const P1*)a.ar_msm, (const XYZZ<G2F>*)a.bs2_msm, (const P1*)a.k_msm,
                                               (const P1*)a.z_msm, (const P1*)a.pok_msm, (const P1*)a.tmp,
@@ -409,6 +437,17 @@ struct CurveImpl : CurveBackend {
     unsigned blocks = (unsigned)((n + 31) / 32);
     if (group == 1) k_dbg_ec<G1F, Fr><<<blocks, 32, 0, s>>>(op, a, b, out, n);
     else k_dbg_ec<G2F, Fr><<<blocks, 32, 0, s>>>(op, a, b, out, n);
+    B200_CUDA(cudaGetLastError());
+  }
+
+  void fixed_base(int group, const void* d_base, const void* d_scalars, uint64_t n, void* d_out,
+                  cudaStream_t s) override {
+    if (!n) return;
+    unsigned blocks = (unsigned)((n + 63) / 64);
+    if (group == 1)
+      k_fixed_base<G1F, Fr><<<blocks, 64, 0, s>>>((const Affine<G1F>*)d_base, (const FrEl*)d_scalars, n, (Affine<G1F>*)d_out);
+    else
+      k_fixed_base<G2F, Fr><<<blocks, 64, 0, s>>>((const Affine<G2F>*)d_base, (const FrEl*)d_scalars, n, (Affine<G2F>*)d_out);
     B200_CUDA(cudaGetLastError());
   }
 

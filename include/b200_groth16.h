@@ -150,6 +150,18 @@ B200_API int b200_kzg_srs_release(uint64_t handle);
 B200_API int b200_blob_commit(uint64_t srs, const uint8_t* blob /* npoints*32 bytes */, uint8_t commitment_out[48],
                               int device);
 
+/* ---- setup building block / instrumentation -----------------------------------------------------
+ * out[i] = [k_i] base as affine points: the fixed-base batch scalar multiplication groth16.Setup is
+ * made of (prover/setup.go:15-28 -> groth16.Setup).  Device pointers. */
+B200_API int b200_fixed_base_dev(int curve, int group, const void* d_base_affine, const void* d_scalars_mont, uint64_t n,
+                                 void* d_out_affine, void* cuda_stream);
+/* number of this library's kernels launched so far in the process */
+B200_API uint64_t b200_launch_count(void);
+/* CUDA-event kernel timers: tags 0 = G1 bucket accumulation, 1 = G2 bucket accumulation, 2 = NTT pass,
+ * 3 = whole G1 MSM, 4 = whole G2 MSM.  collect() synchronises, sums ms / launch counts per tag, clears. */
+B200_API int b200_profile_enable(int on);
+B200_API int b200_profile_collect(double ms_out[5], uint64_t count_out[5]);
+
 /* ---- debug / parity entry points (device pointers; element-wise over n items) ---------------
  * field: 0 = Fp, 1 = Fr, 2 = Fp2 ; op: 0 add, 1 sub, 2 mul, 3 sqr, 4 from_mont, 5 to_mont, 6 inv, 7 neg */
 B200_API int b200_dbg_field_op_dev(int curve, int field, int op, const void* d_a, const void* d_b, void* d_out, uint64_t n,

@@ -1,0 +1,86 @@
+"""CPU: host-side logic that needs no GPU - C ABI exports vs the header, curve constants vs the
+oracle, layouts, MSM planning, the R1CS solver mirror."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from davinci_node_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "b200_groth16.h")).read()
+    declared = set(re.findall(r"B200_API\s+[\w\s\*]+?\b(b200_\w+)\s*\(", hdr))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(capi.lib, name), "missing export " + name
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+
+
+def test_no_gpu_means_loud_failure():
+    """Without a visible GPU the backend must refuse to work (no CPU fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from davinci_node_b200 import capi
+    with pytest.raises(capi.B200Error):
+        capi.init()
+
+
+def test_curve_constants_match_oracle():
+    from davinci_node_b200 import curve_consts, layout
+    from oracle import curve as OC
+    from oracle import params as OP
+    from oracle import ntt as N
+    for cid, c in OP.BY_ID.items():
+        cx = OC.ctx(c.name)
+        k = curve_consts.CONSTS[cid]
+        assert k["g1"] == cx.g1 and k["g2"] == cx.g2
+        L = layout.Layout(cid)
+        assert (L.p, L.r, L.fp_l, L.fr_l) == (c.p, c.r, c.fp_limbs64, c.fr_limbs64)
+        dom = N.Domain(c, 1 << 10)
+        assert curve_consts.domain_constants(cid, 10) == (dom.omega, dom.g)
+
+
+def test_layout_round_trip():
+    from davinci_node_b200 import layout
+    from oracle import curve as OC
+    for name in ("bn254", "bw6_761"):
+        L = layout.Layout(name)
+        cx = OC.ctx(name)
+        pts1 = [cx.g1, None, cx.G1.mul(cx.g1, 5)]
+        pts2 = [cx.g2, None, cx.G2.mul(cx.g2, 7)]
+        assert L.dec_affine(L.enc_affine(pts1, 1), 1) == pts1
+        assert L.dec_affine(L.enc_affine(pts2, 2), 2) == pts2
+        assert len(L.enc_affine(pts2, 2)) == 3 * L.affine_bytes(2)
+        assert L.dec_fr(L.enc_fr([0, 1, L.r - 1])) == [0, 1, L.r - 1]
+        # gnark Montgomery form: 1 encodes as R mod r, little-endian
+        one = int.from_bytes(bytes(L.enc_fr([1])), "little")
+        assert one == (1 << (64 * L.fr_l)) % L.r
+
+
+def test_msm_plan():
+    from davinci_node_b200 import capi
+    p = capi.msm_plan(2, 1 << 22)
+    assert p["nwin"] * p["c"] >= 254 and p["nb"] == 1 << (p["c"] - 1)
+    assert capi.msm_plan(4, 1 << 22)["nwin"] * capi.msm_plan(4, 1 << 22)["c"] >= 378
+    assert capi.msm_plan(3, 4096, 8) == dict(c=8, nwin=32, nb=128, task=p["task"] if False else capi.msm_plan(3, 4096, 8)["task"], group=capi.msm_plan(3, 4096, 8)["group"])
+
+
+def test_solver_mirror_and_witness_errors():
+    from davinci_node_b200 import gnark_types as T
+    from oracle import groth16 as OG
+    from oracle import params as OP
+    from oracle_bridge import ccs_from_oracle
+    q = OP.BN254.r
+    cs, W = OG.synthetic_circuit(20, 3, q, seed=2)
+    ccs = ccs_from_oracle(cs, 1)
+    w = T.Witness(1, W[1:cs.nb_public], W[cs.nb_public:cs.nb_public + ccs.nb_secret])
+    sol = ccs.solve(w)
+    assert sol.values == W
+    a, b, c = OG.constraint_values(cs, W, q)
+    from davinci_node_b200.layout import Layout
+    assert Layout(1).dec_fr(sol.A) == a and Layout(1).dec_fr(sol.C) == c
+    with pytest.raises(ValueError):
+        ccs.solve(T.Witness(1, W[1:2], []))
