@@ -60,7 +60,7 @@ struct DevBuf {
 
 // Scratch for one MSM in flight (one per stream).
 struct MsmWorkspace {
-  DevBuf hist, off, cur, sorted, buckets, tasks, obuckets, partial, groups, windows, ctr;
+  DevBuf hist, off, cur, sorted, buckets, tasks, obuckets, partial, groups, windows, ctr, perm, bins;
 };
 
 struct MsmStats {

@@ -204,9 +204,12 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   Pt* groups = (Pt*)ws.groups.get((uint64_t)pl.nwin * ngroups * sizeof(Pt));
   Pt* windows = (Pt*)ws.windows.get((uint64_t)pl.nwin * sizeof(Pt));
   OvfCounters* ctr = (OvfCounters*)ws.ctr.get(sizeof(OvfCounters));
+  uint32_t* perm = (uint32_t*)ws.perm.get(total_b * 4);
+  uint32_t* bins = (uint32_t*)ws.bins.get(2 * kSizeBins * 4);   // [bins | cursor]
 
   B200_CUDA(cudaMemsetAsync(hist, 0, total_b * 4, s));
   B200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(OvfCounters), s));
+  B200_CUDA(cudaMemsetAsync(bins, 0, 2 * kSizeBins * 4, s));
   const auto* sc = reinterpret_cast<const typename Fr::El*>(d_scalars);
   const auto* pts = reinterpret_cast<const Affine<F>*>(d_points);
   const unsigned sblocks = (unsigned)((n + 255) / 256);
@@ -214,9 +217,14 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, d_index_map);
   k_msm_scan<<<pl.nwin, 1024, 0, s>>>(hist, pl, off, cur);
   k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, d_index_map);
+  // size-sorted bucket schedule
+  const unsigned szblocks = (unsigned)((total_b + kSizeThreads * kSizePerThread - 1) / (kSizeThreads * kSizePerThread));
+  k_msm_size_hist<<<szblocks, kSizeThreads, 0, s>>>(off, cur, total_b, bins);
+  k_msm_size_scan<<<1, kSizeBins, 0, s>>>(bins, bins + kSizeBins);
+  k_msm_size_scatter<<<szblocks, kSizeThreads, 0, s>>>(off, cur, total_b, bins + kSizeBins, perm);
   const int tok_acc = prof_begin(GROUP == 2 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1, s);
-  k_msm_accumulate<F><<<(unsigned)((total_b + 127) / 128), 128, 0, s>>>(pts, sorted, off, cur, pl, buckets, tasks,
-                                                                         obuckets, ctr);
+  k_msm_accumulate<F><<<(unsigned)((total_b + 127) / 128), 128, 0, s>>>(pts, sorted, off, cur, perm, pl, buckets,
+                                                                         tasks, obuckets, ctr);
   prof_end(tok_acc, s);
   // oversized buckets (skewed scalar distributions, e.g. the many 1-valued witness wires)
   unsigned ovf_blocks = (unsigned)std::min<uint64_t>((pl.max_ovf + 127) / 128, 148 * 8);
@@ -228,7 +236,7 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   k_msm_window_sum<F><<<pl.nwin, kReduceThreads, red_smem, s>>>(groups, pl, windows);
   k_msm_horner<F><<<1, 32, 0, s>>>(windows, pl, (Pt*)d_out);
   prof_end(tok_total, s);
-  prof_count_launches(9);
+  prof_count_launches(12);
   B200_CUDA(cudaGetLastError());
 }
 

@@ -162,33 +162,103 @@ __device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const Affine<F>* __
   }
 }
 
+// ---- schedule: counting sort of the buckets by (clamped) size, largest first, so that the 32
+// buckets of a warp have equal trip counts (no divergence) and the heavy buckets start first (no tail)
+constexpr int kSizeBins = 1024;
+constexpr int kSizeThreads = 1024;
+constexpr int kSizePerThread = 8;
+
+static __device__ __forceinline__ uint32_t size_bin(uint32_t cnt) { return cnt < kSizeBins ? cnt : kSizeBins - 1; }
+
+static __global__ void __launch_bounds__(kSizeThreads)
+k_msm_size_hist(const uint32_t* __restrict__ off, const uint32_t* __restrict__ end, uint64_t total_b,
+                uint32_t* __restrict__ bins) {
+  __shared__ uint32_t sh[kSizeBins];
+  for (int b = threadIdx.x; b < kSizeBins; b += kSizeThreads) sh[b] = 0;
+  __syncthreads();
+  uint64_t base = (uint64_t)blockIdx.x * kSizeThreads * kSizePerThread;
+  for (int k = 0; k < kSizePerThread; k++) {
+    uint64_t gb = base + (uint64_t)k * kSizeThreads + threadIdx.x;
+    if (gb < total_b) atomicAdd(&sh[size_bin(end[gb] - off[gb])], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < kSizeBins; b += kSizeThreads)
+    if (sh[b]) atomicAdd(&bins[b], sh[b]);
+}
+
+// cursor[b] = number of buckets in strictly larger bins (descending order); single block
+static __global__ void __launch_bounds__(kSizeBins) k_msm_size_scan(const uint32_t* __restrict__ bins,
+                                                                     uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t sh[kSizeBins];
+  int t = threadIdx.x;
+  sh[t] = bins[kSizeBins - 1 - t];   // reversed: index 0 = largest bin
+  __syncthreads();
+  for (int d = 1; d < kSizeBins; d <<= 1) {
+    uint32_t v = t >= d ? sh[t - d] : 0;
+    __syncthreads();
+    sh[t] += v;
+    __syncthreads();
+  }
+  cursor[kSizeBins - 1 - t] = sh[t] - bins[kSizeBins - 1 - t];   // exclusive
+}
+
+static __global__ void __launch_bounds__(kSizeThreads)
+k_msm_size_scatter(const uint32_t* __restrict__ off, const uint32_t* __restrict__ end, uint64_t total_b,
+                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ perm) {
+  __shared__ uint32_t cnt[kSizeBins];
+  __shared__ uint32_t basep[kSizeBins];
+  for (int b = threadIdx.x; b < kSizeBins; b += kSizeThreads) cnt[b] = 0;
+  __syncthreads();
+  uint64_t base = (uint64_t)blockIdx.x * kSizeThreads * kSizePerThread;
+  uint32_t mybin[kSizePerThread], mypos[kSizePerThread];
+  for (int k = 0; k < kSizePerThread; k++) {
+    uint64_t gb = base + (uint64_t)k * kSizeThreads + threadIdx.x;
+    mybin[k] = 0xffffffffu;
+    if (gb < total_b) {
+      mybin[k] = size_bin(end[gb] - off[gb]);
+      mypos[k] = atomicAdd(&cnt[mybin[k]], 1u);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < kSizeBins; b += kSizeThreads)
+    basep[b] = cnt[b] ? atomicAdd(&cursor[b], cnt[b]) : 0;
+  __syncthreads();
+  for (int k = 0; k < kSizePerThread; k++) {
+    uint64_t gb = base + (uint64_t)k * kSizeThreads + threadIdx.x;
+    if (mybin[k] != 0xffffffffu) perm[basep[mybin[k]] + mypos[k]] = (uint32_t)gb;
+  }
+}
+
+constexpr uint32_t kOvfTask = kOvfTaskPoints;
+
 template <class F>
 __global__ void __launch_bounds__(128)
 k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted,
-                 const uint32_t* __restrict__ off, const uint32_t* __restrict__ end, MsmPlan pl,
-                 XYZZ<F>* __restrict__ buckets, OvfTask* __restrict__ tasks, OvfBucket* __restrict__ obuckets,
-                 OvfCounters* __restrict__ ctr) {
-  uint64_t gb = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gb >= (uint64_t)pl.nwin * pl.nb) return;
-  uint32_t w = (uint32_t)(gb / pl.nb);
+                 const uint32_t* __restrict__ off, const uint32_t* __restrict__ end,
+                 const uint32_t* __restrict__ perm, MsmPlan pl, XYZZ<F>* __restrict__ buckets,
+                 OvfTask* __restrict__ tasks, OvfBucket* __restrict__ obuckets, OvfCounters* __restrict__ ctr) {
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)pl.nwin * pl.nb) return;
+  const uint32_t gb = perm[t];
+  uint32_t w = gb / pl.nb;
   uint32_t start = off[gb], cnt = end[gb] - start;
   uint32_t mine = cnt;
   if (cnt > pl.task) {
     mine = pl.task;
-    uint32_t extra = (cnt - pl.task + pl.task - 1) / pl.task;
+    uint32_t extra = (cnt - pl.task + kOvfTask - 1) / kOvfTask;
     uint32_t first = atomicAdd(&ctr->ntasks, extra);
     if (first + extra <= pl.max_ovf) {
       uint32_t ob = atomicAdd(&ctr->nbuckets, 1u);
-      obuckets[ob] = OvfBucket{(uint32_t)gb, first, extra, 0};
+      obuckets[ob] = OvfBucket{gb, first, extra, 0};
       uint32_t s = start + pl.task, left = cnt - pl.task;
-      for (uint32_t t = 0; t < extra; t++) {
-        uint32_t l = left < pl.task ? left : pl.task;
-        tasks[first + t] = OvfTask{(uint32_t)gb, s, l, 0};
+      for (uint32_t k = 0; k < extra; k++) {
+        uint32_t l = left < kOvfTask ? left : kOvfTask;
+        tasks[first + k] = OvfTask{gb, s, l, 0};
         s += l;
         left -= l;
       }
     } else {
-      mine = cnt;   // cannot happen (capacity is n*nwin/task + nwin*nb); stay correct anyway
+      mine = cnt;   // cannot happen (capacity is n*nwin/kOvfTask + 1); stay correct anyway
     }
   }
   XYZZ<F> acc;

@@ -7,6 +7,8 @@
 
 namespace b200 {
 
+constexpr uint32_t kOvfTaskPoints = 128;   // points per overflow task (their latency is serial)
+
 struct MsmPlan {
   uint64_t n;          // number of (point, scalar) pairs
   int c;               // window width in bits
@@ -37,13 +39,13 @@ inline MsmPlan make_msm_plan(uint64_t n, int scalar_bits, int c_override) {
   pl.nwin = (scalar_bits + 1 + pl.c - 1) / pl.c;
   pl.nb = 1u << (pl.c - 1);
   uint64_t avg = n / pl.nb + 1;
-  pl.task = (uint32_t)std::max<uint64_t>(64, 4 * avg);
+  pl.task = (uint32_t)std::max<uint64_t>(256, 4 * avg);
   uint64_t total_b = (uint64_t)pl.nwin * pl.nb;
   uint32_t g = 1;
   while (g * 2 <= 64 && (uint64_t)g * 2 * 16384 <= total_b) g *= 2;
   if (g < 4) g = std::min<uint32_t>(4, pl.nb);
   pl.group = std::min<uint32_t>(g, pl.nb);
-  pl.max_ovf = (uint32_t)((n * (uint64_t)pl.nwin) / pl.task + 1);
+  pl.max_ovf = (uint32_t)((n * (uint64_t)pl.nwin) / kOvfTaskPoints + 1);
   return pl;
 }
 
