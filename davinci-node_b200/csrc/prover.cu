@@ -37,18 +37,30 @@ void upload(DevBuf& buf, const void* src, size_t bytes, cudaStream_t s) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------ PkInstance
-PkInstance::PkInstance(int dev) : device(dev) {
+PkSlot::PkSlot(int dev) : device(dev) {
   DeviceScope ds(dev);
   for (auto& s : st) B200_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   for (auto& e : ev) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
-PkInstance::~PkInstance() {
+PkSlot::~PkSlot() {
   cudaSetDevice(device);
   for (auto& s : st)
     if (s) cudaStreamDestroy(s);
   for (auto& e : ev)
     if (e) cudaEventDestroy(e);
+}
+
+PkInstance::PkInstance(int dev) : device(dev) {
+  for (int i = 0; i < kSlotsPerDevice; i++) slots.emplace_back(new PkSlot(dev));
+}
+
+PkSlot& PkInstance::acquire() {
+  for (auto& s : slots)
+    if (s->mu.try_lock()) return *s;
+  PkSlot& s = *slots[next_slot.fetch_add(1) % slots.size()];
+  s.mu.lock();
+  return s;
 }
 
 // ------------------------------------------------------------------------------------ registration
@@ -124,7 +136,7 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
   for (int dev : devices) {
     DeviceScope ds(dev);
     std::unique_ptr<PkInstance> in(new PkInstance(dev));
-    cudaStream_t s = in->st[0];
+    cudaStream_t s = in->slots[0]->st[0];
     auto put_ext = [&](DevBuf& buf, const b200_slice& sl, size_t pb, const void* e0, const void* e1) {
       uint8_t* p = (uint8_t*)buf.get((sl.len + 2) * pb);
       if (sl.len) B200_CUDA(cudaMemcpyAsync(p, sl.ptr, sl.len * pb, cudaMemcpyHostToDevice, s));
@@ -156,16 +168,18 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
     B200_CUDA(cudaMemcpyAsync(gens + frb, d.coset_gen, frb, cudaMemcpyHostToDevice, s));
     cb->domain_init(in->dom, pk->logn, gens, gens + frb, s);
     // ---- per-proof workspace
-    in->W.get((pk->m + 4) * frb);
-    in->a.get(pk->n * frb);
-    in->b.get(pk->n * frb);
-    in->c.get(pk->n * frb);
-    in->rs.get(2 * frb);
-    in->cvals.get(std::max<uint64_t>(total_sigma, 1) * frb);
-    in->chal.get(frb);
-    in->msm_out.get(6 * cb->xyzz_bytes(2));
-    in->tmp.get(2 * cb->xyzz_bytes(1));
-    in->out_aff.get(3 * g1b + g2b);
+    for (auto& sl : in->slots) {
+      sl->W.get((pk->m + 4) * frb);
+      sl->a.get(pk->n * frb);
+      sl->b.get(pk->n * frb);
+      sl->c.get(pk->n * frb);
+      sl->rs.get(2 * frb);
+      sl->cvals.get(std::max<uint64_t>(total_sigma, 1) * frb);
+      sl->chal.get(frb);
+      sl->msm_out.get(6 * cb->xyzz_bytes(2));
+      sl->tmp.get(2 * cb->xyzz_bytes(1));
+      sl->out_aff.get(3 * g1b + g2b);
+    }
     B200_CUDA(cudaStreamSynchronize(s));
     pk->inst.push_back(std::move(in));
   }
@@ -185,7 +199,8 @@ PkInstance& ProvingKeyDev::pick(int device) {
 // ------------------------------------------------------------------------------------ prove
 void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, int device, bool inputs_on_device) {
   PkInstance& I = pick(device);
-  std::lock_guard<std::mutex> lk(I.mu);
+  PkSlot& S = I.acquire();
+  std::lock_guard<std::mutex> lk(S.mu, std::adopt_lock);
   DeviceScope ds(I.device);
   const size_t frb = cb->fr_bytes(), g1b = cb->affine_bytes(1), g2b = cb->affine_bytes(2);
   const size_t x1 = cb->xyzz_bytes(1), x2 = cb->xyzz_bytes(2);
@@ -195,32 +210,32 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   if (in.nb_commitments != commit_n.size()) throw std::runtime_error("nb_commitments mismatch with proving key");
   if (!in.r || !in.s) throw std::runtime_error("r / s missing");
   const cudaMemcpyKind kind = inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  cudaStream_t s0 = I.st[0], s1 = I.st[1], s2 = I.st[2];
-  uint8_t* W = (uint8_t*)I.W.p;
-  uint8_t* a = (uint8_t*)I.a.p;
-  uint8_t* b = (uint8_t*)I.b.p;
-  uint8_t* c = (uint8_t*)I.c.p;
+  cudaStream_t s0 = S.st[0], s1 = S.st[1], s2 = S.st[2];
+  uint8_t* W = (uint8_t*)S.W.p;
+  uint8_t* a = (uint8_t*)S.a.p;
+  uint8_t* b = (uint8_t*)S.b.p;
+  uint8_t* c = (uint8_t*)S.c.p;
 
   // ---- inputs (s0): wire vector first so the A / B MSMs can start while a, b, c are still arriving
   B200_CUDA(cudaMemcpyAsync(W, in.wires.ptr, m * frb, kind, s0));
-  uint8_t* rs_in = (uint8_t*)I.rs.p;
+  uint8_t* rs_in = (uint8_t*)S.rs.p;
   B200_CUDA(cudaMemcpyAsync(rs_in, in.r, frb, kind, s0));
   B200_CUDA(cudaMemcpyAsync(rs_in + frb, in.s, frb, kind, s0));
   cb->prep_rs(rs_in, rs_in + frb, W + m * frb, s0);
-  B200_CUDA(cudaEventRecord(I.ev[0], s0));
+  B200_CUDA(cudaEventRecord(S.ev[0], s0));
 
-  uint8_t* mo = (uint8_t*)I.msm_out.p;   // [ar, bs1, k, z, pok] G1 then bs2 G2
+  uint8_t* mo = (uint8_t*)S.msm_out.p;   // [ar, bs1, k, z, pok] G1 then bs2 G2
   uint8_t *o_ar = mo, *o_bs1 = mo + x1, *o_k = mo + 2 * x1, *o_z = mo + 3 * x1, *o_pok = mo + 4 * x1,
           *o_bs2 = mo + 5 * x1;
 
   // ---- s1: Ar, Bs1   s2: Bs (G2)
-  B200_CUDA(cudaStreamWaitEvent(s1, I.ev[0], 0));
-  cb->msm(1, I.A.p, W, m + 4, o_ar, I.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapA.p);
-  cb->msm(1, I.B1.p, W, m + 4, o_bs1, I.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapB.p);
-  B200_CUDA(cudaEventRecord(I.ev[1], s1));
-  B200_CUDA(cudaStreamWaitEvent(s2, I.ev[0], 0));
-  cb->msm(2, I.B2.p, W, m + 4, o_bs2, I.ws[2], s2, 0, nullptr, (const uint32_t*)I.mapB.p);
-  B200_CUDA(cudaEventRecord(I.ev[2], s2));
+  B200_CUDA(cudaStreamWaitEvent(s1, S.ev[0], 0));
+  cb->msm(1, I.A.p, W, m + 4, o_ar, S.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapA.p);
+  cb->msm(1, I.B1.p, W, m + 4, o_bs1, S.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapB.p);
+  B200_CUDA(cudaEventRecord(S.ev[1], s1));
+  B200_CUDA(cudaStreamWaitEvent(s2, S.ev[0], 0));
+  cb->msm(2, I.B2.p, W, m + 4, o_bs2, S.ws[2], s2, 0, nullptr, (const uint32_t*)I.mapB.p);
+  B200_CUDA(cudaEventRecord(S.ev[2], s2));
 
   // ---- s0: quotient, Z and K MSMs, proof of knowledge
   const uint64_t nc = in.a.len;
@@ -235,12 +250,12 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
     B200_CUDA(cudaMemcpyAsync(c, in.c.ptr, nc * frb, kind, s0));
   }
   cb->compute_h(I.dom, a, b, c, s0);
-  cb->msm(1, I.Z.p, a, nZ, o_z, I.ws[0], s0, 0, nullptr, nullptr);
-  cb->msm(1, I.K.p, W + nb_public * frb, m - nb_public + 4, o_k, I.ws[0], s0, 0, nullptr,
+  cb->msm(1, I.Z.p, a, nZ, o_z, S.ws[0], s0, 0, nullptr, nullptr);
+  cb->msm(1, I.K.p, W + nb_public * frb, m - nb_public + 4, o_k, S.ws[0], s0, 0, nullptr,
           (const uint32_t*)I.mapK.p);
   bool have_pok = total_commit > 0 || !commit_n.empty();
   if (have_pok) {
-    uint8_t* cv = (uint8_t*)I.cvals.p;
+    uint8_t* cv = (uint8_t*)S.cvals.p;
     uint64_t off = 0;
     for (size_t i = 0; i < commit_n.size(); i++) {
       if (in.priv_committed[i].len != commit_n[i])
@@ -248,7 +263,7 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
       if (commit_n[i]) B200_CUDA(cudaMemcpyAsync(cv + off * frb, in.priv_committed[i].ptr, commit_n[i] * frb, kind, s0));
       if (i >= 1) {
         if (!in.fold_challenge) throw std::runtime_error("fold_challenge required with more than one commitment");
-        if (i == 1) B200_CUDA(cudaMemcpyAsync(I.chal.p, in.fold_challenge, frb, kind, s0));
+        if (i == 1) B200_CUDA(cudaMemcpyAsync(S.chal.p, in.fold_challenge, frb, kind, s0));
         // segment i is scaled by challenge^i : scale every later segment once per step
       }
       off += commit_n[i];
@@ -256,15 +271,15 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
     // scale segments [i..] by the challenge, for i = 1 .. k-1  => segment j picks up challenge^j
     off = 0;
     for (size_t i = 0; i < commit_n.size(); i++) {
-      if (i >= 1) cb->scale_vec(cv + off * frb, I.chal.p, total_commit - off, s0);
+      if (i >= 1) cb->scale_vec(cv + off * frb, S.chal.p, total_commit - off, s0);
       off += commit_n[i];
     }
-    cb->msm(1, I.sigma_all.p, cv, total_commit, o_pok, I.ws[0], s0, 0, nullptr, nullptr);
+    cb->msm(1, I.sigma_all.p, cv, total_commit, o_pok, S.ws[0], s0, 0, nullptr, nullptr);
   }
-  B200_CUDA(cudaStreamWaitEvent(s0, I.ev[1], 0));
-  B200_CUDA(cudaStreamWaitEvent(s0, I.ev[2], 0));
+  B200_CUDA(cudaStreamWaitEvent(s0, S.ev[1], 0));
+  B200_CUDA(cudaStreamWaitEvent(s0, S.ev[2], 0));
 
-  uint8_t* oa = (uint8_t*)I.out_aff.p;   // ar, krs, pok (G1), bs (G2)
+  uint8_t* oa = (uint8_t*)S.out_aff.p;   // ar, krs, pok (G1), bs (G2)
   AssembleArgs aa{};
   aa.ar_msm = o_ar;
   aa.bs1_msm = o_bs1;
@@ -273,7 +288,7 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   aa.z_msm = o_z;
   aa.pok_msm = have_pok ? o_pok : nullptr;
   aa.rs = W + m * frb;
-  aa.tmp = I.tmp.p;
+  aa.tmp = S.tmp.p;
   aa.out_ar = oa;
   aa.out_krs = oa + g1b;
   aa.out_pok = oa + 2 * g1b;
@@ -293,16 +308,17 @@ void ProvingKeyDev::commit(uint32_t i, const b200_slice& values, void* out_affin
   if (i >= commit_n.size()) throw std::runtime_error("commitment index out of range");
   if (values.len != commit_n[i]) throw std::runtime_error("commit: values length mismatch with Basis");
   PkInstance& I = pick(device);
-  std::lock_guard<std::mutex> lk(I.mu);
+  PkSlot& S = I.acquire();
+  std::lock_guard<std::mutex> lk(S.mu, std::adopt_lock);
   DeviceScope ds(I.device);
   const size_t frb = cb->fr_bytes(), g1b = cb->affine_bytes(1);
-  cudaStream_t s0 = I.st[0];
-  uint8_t* cv = (uint8_t*)I.cvals.p;
+  cudaStream_t s0 = S.st[0];
+  uint8_t* cv = (uint8_t*)S.cvals.p;
   if (values.len) B200_CUDA(cudaMemcpyAsync(cv, values.ptr, values.len * frb, cudaMemcpyHostToDevice, s0));
-  uint8_t* mo = (uint8_t*)I.msm_out.p;
-  cb->msm(1, I.basis[i]->p, cv, values.len, mo, I.ws[0], s0, 0, nullptr, nullptr);
-  cb->to_affine(1, mo, I.out_aff.p, 1, s0);
-  B200_CUDA(cudaMemcpyAsync(out_affine, I.out_aff.p, g1b, cudaMemcpyDeviceToHost, s0));
+  uint8_t* mo = (uint8_t*)S.msm_out.p;
+  cb->msm(1, I.basis[i]->p, cv, values.len, mo, S.ws[0], s0, 0, nullptr, nullptr);
+  cb->to_affine(1, mo, S.out_aff.p, 1, s0);
+  B200_CUDA(cudaMemcpyAsync(out_affine, S.out_aff.p, g1b, cudaMemcpyDeviceToHost, s0));
   B200_CUDA(cudaStreamSynchronize(s0));
 }
 

@@ -10,20 +10,33 @@
 
 namespace b200 {
 
-// One copy of a proving key on one GPU, with the workspace for one proof in flight.
-struct PkInstance {
+// Workspace + streams for ONE proof in flight.  A key instance owns several slots so that the
+// latency-bound tails of one proof (Horner, bucket reduction, assembly, copies) overlap the
+// accumulation kernels of the next one.
+struct PkSlot {
   int device;
   std::mutex mu;
   cudaStream_t st[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  DevBuf W, a, b, c, rs, cvals, chal, msm_out, tmp, out_aff;
+  MsmWorkspace ws[3];
+  explicit PkSlot(int dev);
+  ~PkSlot();
+};
+
+constexpr int kSlotsPerDevice = 2;
+
+// One copy of a proving key on one GPU.
+struct PkInstance {
+  int device;
   DevBuf A, B1, B2, K, Z, mapA, mapB, mapK, sigma_all, gens;
   std::vector<std::unique_ptr<DevBuf>> basis;
   NttDomain dom;
-  // per-proof workspace
-  DevBuf W, a, b, c, rs, cvals, chal, msm_out, tmp, out_aff;
-  MsmWorkspace ws[3];
+  std::vector<std::unique_ptr<PkSlot>> slots;
+  std::atomic<uint32_t> next_slot{0};
   explicit PkInstance(int dev);
-  ~PkInstance();
+  // returns a slot with its mutex HELD (first free one, else waits on the next in round-robin order)
+  PkSlot& acquire();
 };
 
 struct ProvingKeyDev {
