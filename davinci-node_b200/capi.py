@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200groth16.so")
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "libb200groth16.so")
 
 
 class B200Error(RuntimeError):
@@ -64,6 +64,7 @@ _PROTOS = {
     "b200_prove": (_i, [_u64, C.POINTER(ProveIn), C.POINTER(ProofOut), _i]),
     "b200_prove_dev": (_i, [_u64, C.POINTER(ProveIn), C.POINTER(ProofOut), _i]),
     "b200_fixed_base_dev": (_i, [_i, _i, _vp, _vp, _u64, _vp, _vp]),
+    "b200_sum_partials_dev": (_i, [_i, _i, _vp, _u32, _vp, _vp]),
     "b200_launch_count": (_u64, []),
     "b200_profile_enable": (_i, [_i]),
     "b200_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(_u64)]),

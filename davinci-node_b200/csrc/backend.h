@@ -130,6 +130,8 @@ struct CurveBackend {
   virtual void blob_to_scalars(const void* d_blob, void* d_scalars, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;
   // --- point helpers
   virtual void to_affine(int group, const void* d_xyzz, void* d_affine, uint32_t count, cudaStream_t s) = 0;
+  // affine(sum of count XYZZ points): combine of range-split MSM partials
+  virtual void sum_partials(int group, const void* d_xyzz, uint32_t count, void* d_affine, cudaStream_t s) = 0;
   // out = sum_i [k_i] P_i  (tiny, single thread): used for the alpha/beta/delta terms of the proof
   // --- debug / parity entry points (element-wise, device pointers)
   virtual void dbg_field_op(int field, int op, const void* a, const void* b, void* out, uint64_t n,

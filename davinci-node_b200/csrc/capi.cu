@@ -394,6 +394,14 @@ int b200_fixed_base_dev(int curve_id, int group, const void* d_base_affine, cons
   });
 }
 
+int b200_sum_partials_dev(int curve_id, int group, const void* d_xyzz, uint32_t count, void* d_out_affine,
+                          void* stream) {
+  return guarded([&] {
+    check_group(group);
+    curve(curve_id).sum_partials(group, d_xyzz, count, d_out_affine, (cudaStream_t)stream);
+  });
+}
+
 uint64_t b200_launch_count(void) { return prof_launches(); }
 
 int b200_profile_enable(int on) {

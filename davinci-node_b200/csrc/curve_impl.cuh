@@ -80,6 +80,22 @@ __global__ void k_dbg_ec(int op, const void* a, const void* b, void* out, uint64
   }
 }
 
+// out = affine(sum of `count` XYZZ partial sums): the combine step of a range-split MSM whose per-GPU
+// partials were all-gathered over NVLink (count = number of GPUs, a few hundred bytes each)
+template <class F>
+__global__ void k_sum_partials(const XYZZ<F>* in, uint32_t count, Affine<F>* out) {
+  if (threadIdx.x || blockIdx.x) return;
+  XYZZ<F> acc;
+  EC<F>::set_inf(acc);
+  for (uint32_t i = 0; i < count; i++) {
+    XYZZ<F> p = in[i];
+    EC<F>::add(acc, p);
+  }
+  Affine<F> o;
+  EC<F>::to_affine(o, acc);
+  *out = o;
+}
+
 template <class F>
 __global__ void k_to_affine(const XYZZ<F>* in, Affine<F>* out, uint32_t n) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -404,6 +420,13 @@ struct CurveImpl : CurveBackend {
                                               (const P1*)a.z_msm, (const P1*)a.pok_msm, (const P1*)a.tmp,
                                               (Affine<G1F>*)a.out_ar, (Affine<G2F>*)a.out_bs,
                                               (Affine<G1F>*)a.out_krs, (Affine<G1F>*)a.out_pok);
+    B200_CUDA(cudaGetLastError());
+  }
+
+  void sum_partials(int group, const void* d_xyzz, uint32_t count, void* d_aff, cudaStream_t s) override {
+    if (group == 1) k_sum_partials<G1F><<<1, 1, 0, s>>>((const XYZZ<G1F>*)d_xyzz, count, (Affine<G1F>*)d_aff);
+    else k_sum_partials<G2F><<<1, 1, 0, s>>>((const XYZZ<G2F>*)d_xyzz, count, (Affine<G2F>*)d_aff);
+    prof_count_launches(1);
     B200_CUDA(cudaGetLastError());
   }
 

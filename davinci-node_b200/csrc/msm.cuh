@@ -232,7 +232,10 @@ k_msm_size_scatter(const uint32_t* __restrict__ off, const uint32_t* __restrict_
 constexpr uint32_t kOvfTask = kOvfTaskPoints;
 
 template <class F>
-__global__ void __launch_bounds__(128)
+#ifndef B200_ACC_MIN_BLOCKS
+#define B200_ACC_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, B200_ACC_MIN_BLOCKS)
 k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted,
                  const uint32_t* __restrict__ off, const uint32_t* __restrict__ end,
                  const uint32_t* __restrict__ perm, MsmPlan pl, XYZZ<F>* __restrict__ buckets,

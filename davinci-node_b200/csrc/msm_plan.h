@@ -39,7 +39,7 @@ inline MsmPlan make_msm_plan(uint64_t n, int scalar_bits, int c_override) {
   pl.nwin = (scalar_bits + 1 + pl.c - 1) / pl.c;
   pl.nb = 1u << (pl.c - 1);
   uint64_t avg = n / pl.nb + 1;
-  pl.task = (uint32_t)std::max<uint64_t>(256, 4 * avg);
+  pl.task = (uint32_t)std::max<uint64_t>(256, 8 * avg);
   uint64_t total_b = (uint64_t)pl.nwin * pl.nb;
   uint32_t g = 1;
   while (g * 2 <= 64 && (uint64_t)g * 2 * 16384 <= total_b) g *= 2;

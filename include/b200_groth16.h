@@ -155,6 +155,11 @@ B200_API int b200_blob_commit(uint64_t srs, const uint8_t* blob /* npoints*32 by
  * made of (prover/setup.go:15-28 -> groth16.Setup).  Device pointers. */
 B200_API int b200_fixed_base_dev(int curve, int group, const void* d_base_affine, const void* d_scalars_mont, uint64_t n,
                                  void* d_out_affine, void* cuda_stream);
+/* Combine step of a range-split MSM: out = affine(sum of `count` XYZZ partial sums, one
+ * per GPU, all-gathered over NVLink by the caller).  Replaces nothing in the reference (it has no
+ * multi-GPU path); gnark sums its per-chunk partials the same way on the CPU. */
+B200_API int b200_sum_partials_dev(int curve, int group, const void* d_xyzz, uint32_t count, void* d_out_affine,
+                                   void* cuda_stream);
 /* number of this library's kernels launched so far in the process */
 B200_API uint64_t b200_launch_count(void);
 /* CUDA-event kernel timers: tags 0 = G1 bucket accumulation, 1 = G2 bucket accumulation, 2 = NTT pass,
