@@ -64,6 +64,9 @@ _PROTOS = {
     "b200_prove": (_i, [_u64, C.POINTER(ProveIn), C.POINTER(ProofOut), _i]),
     "b200_prove_dev": (_i, [_u64, C.POINTER(ProveIn), C.POINTER(ProofOut), _i]),
     "b200_fixed_base_dev": (_i, [_i, _i, _vp, _vp, _u64, _vp, _vp]),
+    "b200_bases_create_dev": (_i, [_i, _i, _vp, _u64, _i, C.POINTER(_u64), _vp]),
+    "b200_bases_release": (_i, [_u64]),
+    "b200_msm_bases_dev": (_i, [_u64, _vp, _u64, _vp, _vp, _vp]),
     "b200_sum_partials_dev": (_i, [_i, _i, _vp, _u32, _vp, _vp]),
     "b200_launch_count": (_u64, []),
     "b200_profile_enable": (_i, [_i]),

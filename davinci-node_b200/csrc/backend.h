@@ -63,6 +63,13 @@ struct MsmWorkspace {
   DevBuf hist, off, cur, sorted, buckets, tasks, obuckets, partial, groups, windows, ctr, perm, bins;
 };
 
+// A base-point set with its precomputed window multiples resident in HBM ("table mode", msm_plan.h)
+struct MsmBases {
+  DevBuf tables;      // nwin tables of npts affine points: T_j[i] = 2^(c j) P_i
+  uint64_t npts = 0;
+  int c = 0, nwin = 0, group = 1;
+};
+
 struct MsmStats {
   int c, nwin;
   uint32_t nb, task, group;
@@ -113,7 +120,10 @@ struct CurveBackend {
   // d_index_map (optional): scalar i multiplies points[map[i]]; map[i] == 0xffffffff skips scalar i
   virtual void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out_xyzz,
                    MsmWorkspace& ws, cudaStream_t s, int c_override, MsmStats* stats,
-                   const uint32_t* d_index_map = nullptr) = 0;
+                   const uint32_t* d_index_map = nullptr, const MsmBases* bases = nullptr) = 0;
+  // precompute T_j[i] = 2^(c j) P_i for a base set (window_bits = 0: cost model)
+  virtual void build_tables(MsmBases& b, int group, const void* d_points, uint64_t npts, int window_bits,
+                            cudaStream_t s) = 0;
   // --- NTT / quotient
   virtual void domain_init(NttDomain& d, int logn, const void* d_omega, const void* d_g, cudaStream_t s) = 0;
   // gnark fft.Domain semantics: inverse ? FFTInverse : FFT ; dit ? DIT (bit-reversed in) : DIF ; coset

@@ -125,6 +125,12 @@ uint64_t g_next_handle = 1;
 std::map<uint64_t, std::unique_ptr<DomainHandle>> g_domains;
 std::map<uint64_t, std::shared_ptr<ProvingKeyDev>> g_pks;
 std::map<uint64_t, std::shared_ptr<KzgSrsDev>> g_srs;
+struct BasesHandle {
+  CurveBackend* cb;
+  int device;
+  MsmBases bases;
+};
+std::map<uint64_t, std::shared_ptr<BasesHandle>> g_bases;
 
 std::vector<int> selected_devices() {
   int n = 0;
@@ -399,6 +405,47 @@ int b200_sum_partials_dev(int curve_id, int group, const void* d_xyzz, uint32_t 
   return guarded([&] {
     check_group(group);
     curve(curve_id).sum_partials(group, d_xyzz, count, d_out_affine, (cudaStream_t)stream);
+  });
+}
+
+// ---------------------------------------------------------------------------------- base sets (table mode)
+int b200_bases_create_dev(int curve_id, int group, const void* d_points, uint64_t n, int window_bits,
+                          uint64_t* handle_out, void* stream) {
+  return guarded([&] {
+    check_group(group);
+    if (!handle_out) throw std::runtime_error("null argument");
+    std::shared_ptr<BasesHandle> h(new BasesHandle());
+    h->cb = &curve(curve_id);
+    h->device = current_device();
+    h->cb->build_tables(h->bases, group, d_points, n, window_bits, (cudaStream_t)stream);
+    B200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    std::lock_guard<std::mutex> lk(g_hmu);
+    *handle_out = g_next_handle++;
+    g_bases[*handle_out] = h;
+  });
+}
+
+int b200_bases_release(uint64_t h) {
+  return guarded([&] {
+    std::lock_guard<std::mutex> lk(g_hmu);
+    if (!g_bases.erase(h)) throw std::runtime_error("unknown base-set handle");
+  });
+}
+
+int b200_msm_bases_dev(uint64_t handle, const void* d_scalars, uint64_t n, const uint32_t* d_index_map,
+                       void* d_out_xyzz, void* stream) {
+  return guarded([&] {
+    std::shared_ptr<BasesHandle> h;
+    {
+      std::lock_guard<std::mutex> lk(g_hmu);
+      auto it = g_bases.find(handle);
+      if (it == g_bases.end()) throw std::runtime_error("unknown base-set handle");
+      h = it->second;
+    }
+    if (!d_index_map && n > h->bases.npts) throw std::runtime_error("more scalars than base points");
+    MsmWorkspace& ws = workspace_for(h->device, stream);
+    h->cb->msm(h->bases.group, nullptr, d_scalars, n, d_out_xyzz, ws, (cudaStream_t)stream, 0, nullptr, d_index_map,
+               &h->bases);
   });
 }
 

@@ -196,29 +196,54 @@ __global__ void k_assemble_out(const XYZZ<F1>* ar, const XYZZ<F2>* bs2, const XY
 }
 
 // ------------------------------------------------------------------------------------ MSM driver
+// T_j[i] = 2^(c j) P_i for j < nwin (affine, table j at offset j * npts): one thread per point
+template <class F>
+__global__ void __launch_bounds__(64) k_build_tables(const Affine<F>* __restrict__ base, uint64_t npts, int c, int nwin,
+                                                      Affine<F>* __restrict__ tables) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts) return;
+  Affine<F> p;
+  load16(p, base + i);
+  store16(tables + i, p);
+  XYZZ<F> x;
+  EC<F>::from_affine(x, p);
+  for (int j = 1; j < nwin; j++) {
+    for (int k = 0; k < c; k++) EC<F>::dbl(x);
+    Affine<F> o;
+    EC<F>::to_affine(o, x);
+    store16(tables + (uint64_t)j * npts + i, o);
+    // continue from the normalised point: keeps the coordinates short-lived and exact
+    EC<F>::from_affine(x, o);
+  }
+}
+
 template <class F, class Fr, int GROUP>
 void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d_out, MsmWorkspace& ws,
-                cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map) {
+                cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map, const MsmBases* bases) {
   using Pt = XYZZ<F>;
   if (n >= (1ull << 31)) throw std::runtime_error("msm: n must be < 2^31");
-  MsmPlan pl = make_msm_plan(n, Fr::BITS, c_override);
+  MsmPlan pl = bases ? make_msm_plan_table(n, Fr::BITS, bases->c, bases->npts) : make_msm_plan(n, Fr::BITS, c_override);
   if (stats) *stats = MsmStats{pl.c, pl.nwin, pl.nb, pl.task, pl.group};
   if (n == 0) {
     B200_CUDA(cudaMemsetAsync(d_out, 0, sizeof(Pt), s));
     return;
   }
-  const uint64_t total_b = (uint64_t)pl.nwin * pl.nb;
+  const uint64_t total_b = (uint64_t)pl.bwin * pl.nb;
   const uint32_t ngroups = pl.nb / pl.group;
   uint32_t* hist = (uint32_t*)ws.hist.get(total_b * 4);
   uint32_t* off = (uint32_t*)ws.off.get(total_b * 4);
   uint32_t* cur = (uint32_t*)ws.cur.get(total_b * 4);
-  uint32_t* sorted = (uint32_t*)ws.sorted.get((uint64_t)pl.nwin * n * 4);
+  uint32_t* sorted = (uint32_t*)ws.sorted.get((uint64_t)pl.bwin * pl.stride * 4);
   Pt* buckets = (Pt*)ws.buckets.get(total_b * sizeof(Pt));
   OvfTask* tasks = (OvfTask*)ws.tasks.get((uint64_t)pl.max_ovf * sizeof(OvfTask));
   OvfBucket* obuckets = (OvfBucket*)ws.obuckets.get((uint64_t)pl.max_ovf * sizeof(OvfBucket));
   Pt* partial = (Pt*)ws.partial.get((uint64_t)pl.max_ovf * sizeof(Pt));
-  Pt* groups = (Pt*)ws.groups.get((uint64_t)pl.nwin * ngroups * sizeof(Pt));
-  Pt* windows = (Pt*)ws.windows.get((uint64_t)pl.nwin * sizeof(Pt));
+  // window sums run in one or two slice-sum levels
+  const uint32_t kSlices = 64;
+  const bool two_level = ngroups >= 4 * kSlices;
+  Pt* groups = (Pt*)ws.groups.get(((uint64_t)pl.bwin * ngroups + (uint64_t)pl.bwin * kSlices) * sizeof(Pt));
+  Pt* mids = groups + (uint64_t)pl.bwin * ngroups;
+  Pt* windows = (Pt*)ws.windows.get((uint64_t)pl.bwin * sizeof(Pt));
   OvfCounters* ctr = (OvfCounters*)ws.ctr.get(sizeof(OvfCounters));
   uint32_t* perm = (uint32_t*)ws.perm.get(total_b * 4);
   uint32_t* bins = (uint32_t*)ws.bins.get(2 * kSizeBins * 4);   // [bins | cursor]
@@ -227,11 +252,11 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   B200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(OvfCounters), s));
   B200_CUDA(cudaMemsetAsync(bins, 0, 2 * kSizeBins * 4, s));
   const auto* sc = reinterpret_cast<const typename Fr::El*>(d_scalars);
-  const auto* pts = reinterpret_cast<const Affine<F>*>(d_points);
+  const auto* pts = reinterpret_cast<const Affine<F>*>(bases ? bases->tables.p : d_points);
   const unsigned sblocks = (unsigned)((n + 255) / 256);
   const int tok_total = prof_begin(GROUP == 2 ? PROF_MSM_TOTAL_G2 : PROF_MSM_TOTAL_G1, s);
   k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, d_index_map);
-  k_msm_scan<<<pl.nwin, 1024, 0, s>>>(hist, pl, off, cur);
+  k_msm_scan<<<pl.bwin, 1024, 0, s>>>(hist, pl, off, cur);
   k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, d_index_map);
   // size-sorted bucket schedule
   const unsigned szblocks = (unsigned)((total_b + kSizeThreads * kSizePerThread - 1) / (kSizeThreads * kSizePerThread));
@@ -248,11 +273,16 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   size_t red_smem = kReduceThreads * sizeof(Pt);
   k_msm_ovf_merge<F><<<(unsigned)std::min<uint64_t>(pl.max_ovf, 1024), kReduceThreads, red_smem, s>>>(obuckets, ctr,
                                                                                                       partial, buckets);
-  k_msm_bucket_reduce<F><<<(pl.nwin * ngroups + 63) / 64, 64, 0, s>>>(buckets, pl, groups);
-  k_msm_window_sum<F><<<pl.nwin, kReduceThreads, red_smem, s>>>(groups, pl, windows);
+  k_msm_bucket_reduce<F><<<(pl.bwin * ngroups + 63) / 64, 64, 0, s>>>(buckets, pl, groups);
+  if (two_level) {
+    k_msm_slice_sum<F><<<pl.bwin * kSlices, kReduceThreads, red_smem, s>>>(groups, ngroups / kSlices, mids);
+    k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, s>>>(mids, kSlices, windows);
+  } else {
+    k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, s>>>(groups, ngroups, windows);
+  }
   k_msm_horner<F><<<1, 32, 0, s>>>(windows, pl, (Pt*)d_out);
   prof_end(tok_total, s);
-  prof_count_launches(12);
+  prof_count_launches(two_level ? 13 : 12);
   B200_CUDA(cudaGetLastError());
 }
 
@@ -273,9 +303,27 @@ struct CurveImpl : CurveBackend {
   int fr_bits() const override { return Fr::BITS; }
 
   void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out, MsmWorkspace& ws,
-           cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map) override {
-    if (group == 1) msm_launch<G1F, Fr, 1>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map);
-    else msm_launch<G2F, Fr, 2>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map);
+           cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map,
+           const MsmBases* bases) override {
+    if (bases && bases->group != group) throw std::runtime_error("msm: base tables belong to the other group");
+    if (group == 1) msm_launch<G1F, Fr, 1>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map, bases);
+    else msm_launch<G2F, Fr, 2>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map, bases);
+  }
+
+  void build_tables(MsmBases& b, int group, const void* d_points, uint64_t npts, int window_bits,
+                    cudaStream_t s) override {
+    b.group = group;
+    b.npts = npts;
+    b.c = window_bits > 0 ? window_bits : msm_table_window(npts, Fr::BITS);
+    b.nwin = msm_nwin(Fr::BITS, b.c);
+    if ((uint64_t)b.nwin * npts >= (1ull << 31)) throw std::runtime_error("base set too large for table mode");
+    const size_t pb = affine_bytes(group);
+    void* t = b.tables.get(std::max<uint64_t>(npts, 1) * b.nwin * pb);
+    if (!npts) return;
+    unsigned blocks = (unsigned)((npts + 63) / 64);
+    if (group == 1) k_build_tables<G1F><<<blocks, 64, 0, s>>>((const Affine<G1F>*)d_points, npts, b.c, b.nwin, (Affine<G1F>*)t);
+    else k_build_tables<G2F><<<blocks, 64, 0, s>>>((const Affine<G2F>*)d_points, npts, b.c, b.nwin, (Affine<G2F>*)t);
+    B200_CUDA(cudaGetLastError());
   }
 
   // ---------------------------------------------------------------- NTT

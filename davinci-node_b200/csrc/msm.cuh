@@ -58,7 +58,8 @@ __global__ void k_msm_hist(const typename Fr::El* __restrict__ scalars, MsmPlan 
   if (index_map && index_map[i] == 0xffffffffu) return;
   typename Fr::El s;
   load16(s, scalars + i);
-  for_each_digit<Fr>(s, pl, [&](int w, uint32_t b, bool) { atomicAdd(&hist[(uint64_t)w * pl.nb + b], 1u); });
+  const bool table = pl.bwin == 1;
+  for_each_digit<Fr>(s, pl, [&](int w, uint32_t b, bool) { atomicAdd(&hist[(table ? 0 : (uint64_t)w * pl.nb) + b], 1u); });
 }
 
 // one block per window: exclusive scan of hist -> off (start offsets) and cur (running cursors)
@@ -116,9 +117,12 @@ __global__ void k_msm_scatter(const typename Fr::El* __restrict__ scalars, MsmPl
   }
   typename Fr::El s;
   load16(s, scalars + i);
+  const bool table = pl.bwin == 1;
   for_each_digit<Fr>(s, pl, [&](int w, uint32_t b, bool neg) {
-    uint32_t pos = atomicAdd(&cur[(uint64_t)w * pl.nb + b], 1u);
-    sorted[(uint64_t)w * pl.n + pos] = pidx | (neg ? 0x80000000u : 0u);
+    uint32_t pos = atomicAdd(&cur[(table ? 0 : (uint64_t)w * pl.nb) + b], 1u);
+    // table mode: digit window w reads the precomputed multiple 2^(c w) P, stored at w * npts + i
+    uint32_t entry = table ? (uint32_t)((uint64_t)w * pl.npts + pidx) : pidx;
+    sorted[(table ? 0 : (uint64_t)w * pl.stride) + pos] = entry | (neg ? 0x80000000u : 0u);
   });
 }
 
@@ -241,7 +245,7 @@ k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restric
                  const uint32_t* __restrict__ perm, MsmPlan pl, XYZZ<F>* __restrict__ buckets,
                  OvfTask* __restrict__ tasks, OvfBucket* __restrict__ obuckets, OvfCounters* __restrict__ ctr) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint64_t)pl.nwin * pl.nb) return;
+  if (t >= (uint64_t)pl.bwin * pl.nb) return;
   const uint32_t gb = perm[t];
   uint32_t w = gb / pl.nb;
   uint32_t start = off[gb], cnt = end[gb] - start;
@@ -265,7 +269,7 @@ k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restric
     }
   }
   XYZZ<F> acc;
-  accumulate_run<F>(acc, points, sorted + (uint64_t)w * pl.n + start, mine);
+  accumulate_run<F>(acc, points, sorted + (uint64_t)w * pl.stride + start, mine);
   store16(buckets + gb, acc);
 }
 
@@ -279,7 +283,7 @@ k_msm_ovf_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __res
     OvfTask tk = tasks[t];
     uint32_t w = tk.bucket / pl.nb;
     XYZZ<F> acc;
-    accumulate_run<F>(acc, points, sorted + (uint64_t)w * pl.n + tk.start, tk.len);
+    accumulate_run<F>(acc, points, sorted + (uint64_t)w * pl.stride + tk.start, tk.len);
     store16(partial + t, acc);
   }
 }
@@ -340,7 +344,7 @@ k_msm_bucket_reduce(const XYZZ<F>* __restrict__ buckets, MsmPlan pl, XYZZ<F>* __
   using E = EC<F>;
   uint32_t ngroups = pl.nb / pl.group;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint32_t)pl.nwin * ngroups) return;
+  if (t >= (uint32_t)pl.bwin * ngroups) return;
   uint32_t w = t / ngroups, g = t % ngroups;
   const XYZZ<F>* B = buckets + (uint64_t)w * pl.nb + (uint64_t)g * pl.group;
   XYZZ<F> run, acc;
@@ -362,24 +366,23 @@ k_msm_bucket_reduce(const XYZZ<F>* __restrict__ buckets, MsmPlan pl, XYZZ<F>* __
   store16(groups + t, acc);
 }
 
-// one block per window: windows[w] = sum over its groups
+// block b: out[b] = sum of in[b * per_slice .. (b + 1) * per_slice)   (window sums, in one or two levels)
 template <class F>
 __global__ void __launch_bounds__(kReduceThreads)
-k_msm_window_sum(const XYZZ<F>* __restrict__ groups, MsmPlan pl, XYZZ<F>* __restrict__ windows) {
+k_msm_slice_sum(const XYZZ<F>* __restrict__ in, uint32_t per_slice, XYZZ<F>* __restrict__ out) {
   extern __shared__ uint4 smem_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
   using E = EC<F>;
-  uint32_t ngroups = pl.nb / pl.group;
-  const XYZZ<F>* G = groups + (uint64_t)blockIdx.x * ngroups;
+  const XYZZ<F>* G = in + (uint64_t)blockIdx.x * per_slice;
   XYZZ<F> acc;
   E::set_inf(acc);
-  for (uint32_t g = threadIdx.x; g < ngroups; g += kReduceThreads) {
+  for (uint32_t g = threadIdx.x; g < per_slice; g += kReduceThreads) {
     XYZZ<F> p;
     load16_rw(p, G + g);
     E::add(acc, p);
   }
   block_sum<F, kReduceThreads>(acc, sm);
-  if (threadIdx.x == 0) store16(windows + blockIdx.x, acc);
+  if (threadIdx.x == 0) store16(out + blockIdx.x, acc);
 }
 
 // result = sum_w 2^(c w) windows[w]   (single thread; latency hidden by the other MSM streams)
@@ -389,7 +392,7 @@ __global__ void k_msm_horner(const XYZZ<F>* __restrict__ windows, MsmPlan pl, XY
   if (threadIdx.x || blockIdx.x) return;
   XYZZ<F> acc;
   E::set_inf(acc);
-  for (int w = pl.nwin - 1; w >= 0; w--) {
+  for (int w = pl.bwin - 1; w >= 0; w--) {
     for (int i = 0; i < pl.c; i++) E::dbl(acc);
     XYZZ<F> ws;
     load16_rw(ws, windows + w);

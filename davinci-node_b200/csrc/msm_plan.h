@@ -9,24 +9,64 @@ namespace b200 {
 
 constexpr uint32_t kOvfTaskPoints = 128;   // points per overflow task (their latency is serial)
 
+// Two modes:
+//  * windowed (bwin == nwin): classic Pippenger, one bucket set per scalar window, Horner at the end.
+//  * table (bwin == 1): the base set carries precomputed multiples T_j[i] = 2^(c j) P_i resident in
+//    HBM, so every window's digit adds into ONE shared bucket set - no Horner, nwin times fewer
+//    buckets to reduce, which lets c grow (fewer point additions).
 struct MsmPlan {
-  uint64_t n;          // number of (point, scalar) pairs
+  uint64_t n;          // number of scalars
   int c;               // window width in bits
-  int nwin;            // ceil((scalar_bits + 1) / c)
-  uint32_t nb;         // buckets per window = 2^(c-1)
+  int nwin;            // digit windows = ceil((scalar_bits + 1) / c)
+  int bwin;            // bucket windows: nwin (windowed) or 1 (table mode)
+  uint32_t nb;         // buckets per bucket window = 2^(c-1)
   uint32_t task;       // max points a single thread accumulates for one bucket
   uint32_t group;      // buckets per running-sum group
   uint32_t max_ovf;    // capacity of the overflow task list
+  uint64_t npts;       // table mode: points per table (index of digit window w is w*npts + i)
+  uint64_t stride;     // sorted-index entries reserved per bucket window
 };
+
+inline int msm_nwin(int scalar_bits, int c) { return (scalar_bits + 1 + c - 1) / c; }
+
+// window width for a table-mode base set of npts points (fixed when the tables are built)
+inline int msm_table_window(uint64_t npts, int scalar_bits) {
+  int best_c = 4;
+  double best = 1e300;
+  for (int c = 4; c <= 22; c++) {
+    int nwin = msm_nwin(scalar_bits, c);
+    double nb = std::ldexp(1.0, c - 1);
+    double cost = (double)npts * nwin + nb * 2.0 * 4.0 + 3000.0 * nwin;   // adds + bucket reduction + fixed
+    if ((double)nwin * (double)npts >= 2147483648.0) continue;           // index must fit 31 bits
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
+}
+
+inline void msm_plan_finish(MsmPlan& pl) {
+  pl.nb = 1u << (pl.c - 1);
+  const uint64_t adds = pl.n * (uint64_t)pl.nwin;
+  const uint64_t total_b = (uint64_t)pl.bwin * pl.nb;
+  uint64_t avg = adds / total_b + 1;
+  pl.task = (uint32_t)std::max<uint64_t>(256, 8 * avg);
+  uint32_t g = 1;
+  while (g * 2 <= 64 && (uint64_t)g * 2 * 16384 <= total_b) g *= 2;
+  if (g < 4) g = std::min<uint32_t>(4, pl.nb);
+  pl.group = std::min<uint32_t>(g, pl.nb);
+  pl.max_ovf = (uint32_t)(adds / kOvfTaskPoints + 1);
+  pl.stride = pl.bwin == 1 ? adds : pl.n;
+}
 
 inline MsmPlan make_msm_plan(uint64_t n, int scalar_bits, int c_override) {
   MsmPlan pl{};
   pl.n = n;
   int best_c = 2;
   double best = 1e300;
-  int cmax = 16;
-  for (int c = 2; c <= cmax; c++) {
-    int nwin = (scalar_bits + 1 + c - 1) / c;
+  for (int c = 2; c <= 16; c++) {
+    int nwin = msm_nwin(scalar_bits, c);
     double nb = std::ldexp(1.0, c - 1);
     // mixed adds for accumulation + ~3x weight for the (full-add, low-parallelism) bucket reduction
     double cost = (double)n * nwin * 1.0 + nwin * nb * 2.0 * 3.0;
@@ -36,16 +76,21 @@ inline MsmPlan make_msm_plan(uint64_t n, int scalar_bits, int c_override) {
     }
   }
   pl.c = c_override > 0 ? c_override : best_c;
-  pl.nwin = (scalar_bits + 1 + pl.c - 1) / pl.c;
-  pl.nb = 1u << (pl.c - 1);
-  uint64_t avg = n / pl.nb + 1;
-  pl.task = (uint32_t)std::max<uint64_t>(256, 8 * avg);
-  uint64_t total_b = (uint64_t)pl.nwin * pl.nb;
-  uint32_t g = 1;
-  while (g * 2 <= 64 && (uint64_t)g * 2 * 16384 <= total_b) g *= 2;
-  if (g < 4) g = std::min<uint32_t>(4, pl.nb);
-  pl.group = std::min<uint32_t>(g, pl.nb);
-  pl.max_ovf = (uint32_t)((n * (uint64_t)pl.nwin) / kOvfTaskPoints + 1);
+  pl.nwin = msm_nwin(scalar_bits, pl.c);
+  pl.bwin = pl.nwin;
+  pl.npts = 0;
+  msm_plan_finish(pl);
+  return pl;
+}
+
+inline MsmPlan make_msm_plan_table(uint64_t n, int scalar_bits, int c, uint64_t npts) {
+  MsmPlan pl{};
+  pl.n = n;
+  pl.c = c;
+  pl.nwin = msm_nwin(scalar_bits, c);
+  pl.bwin = 1;
+  pl.npts = npts;
+  msm_plan_finish(pl);
   return pl;
 }
 

@@ -137,30 +137,42 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
     DeviceScope ds(dev);
     std::unique_ptr<PkInstance> in(new PkInstance(dev));
     cudaStream_t s = in->slots[0]->st[0];
-    auto put_ext = [&](DevBuf& buf, const b200_slice& sl, size_t pb, const void* e0, const void* e1) {
-      uint8_t* p = (uint8_t*)buf.get((sl.len + 2) * pb);
+    // upload (points || extra0 || extra1) to a staging buffer, build its window tables, drop the staging copy
+    DevBuf stage;
+    auto put_tables = [&](MsmBases& t, int group, const b200_slice& sl, size_t pb, const void* e0, const void* e1) {
+      uint64_t cnt = sl.len + (e0 ? 1 : 0) + (e1 ? 1 : 0);
+      uint8_t* p = (uint8_t*)stage.get(std::max<uint64_t>(cnt, 1) * pb);
       if (sl.len) B200_CUDA(cudaMemcpyAsync(p, sl.ptr, sl.len * pb, cudaMemcpyHostToDevice, s));
-      B200_CUDA(cudaMemcpyAsync(p + sl.len * pb, e0, pb, cudaMemcpyHostToDevice, s));
+      if (e0) B200_CUDA(cudaMemcpyAsync(p + sl.len * pb, e0, pb, cudaMemcpyHostToDevice, s));
       if (e1) B200_CUDA(cudaMemcpyAsync(p + (sl.len + 1) * pb, e1, pb, cudaMemcpyHostToDevice, s));
+      cb->build_tables(t, group, p, cnt, 0, s);
+      B200_CUDA(cudaStreamSynchronize(s));   // staging buffer is reused by the next base set
     };
-    put_ext(in->A, d.g1_A, g1b, d.g1_delta, d.g1_alpha);
-    put_ext(in->B1, d.g1_B, g1b, d.g1_delta, d.g1_beta);
-    put_ext(in->B2, d.g2_B, g2b, d.g2_delta, d.g2_beta);
-    put_ext(in->K, d.g1_K, g1b, d.g1_delta, nullptr);
-    upload(in->Z, d.g1_Z.ptr, d.g1_Z.len * g1b, s);
+    put_tables(in->tA, 1, d.g1_A, g1b, d.g1_delta, d.g1_alpha);
+    put_tables(in->tB1, 1, d.g1_B, g1b, d.g1_delta, d.g1_beta);
+    put_tables(in->tB2, 2, d.g2_B, g2b, d.g2_delta, d.g2_beta);
+    put_tables(in->tK, 1, d.g1_K, g1b, d.g1_delta, nullptr);
+    put_tables(in->tZ, 1, d.g1_Z, g1b, nullptr, nullptr);
     upload(in->mapA, mapA.data(), mapA.size() * 4, s);
     upload(in->mapB, mapB.data(), mapB.size() * 4, s);
     upload(in->mapK, mapK.data(), mapK.size() * 4, s);
-    in->basis.resize(d.nb_commitments);
-    uint8_t* sg = (uint8_t*)in->sigma_all.get(std::max<uint64_t>(total_sigma, 1) * g1b);
-    uint64_t off = 0;
+    in->tBasis.resize(d.nb_commitments);
+    {
+      // concatenated sigma bases -> one table set
+      uint8_t* sg = (uint8_t*)stage.get(std::max<uint64_t>(total_sigma, 1) * g1b);
+      uint64_t off = 0;
+      for (uint32_t i = 0; i < d.nb_commitments; i++) {
+        if (pk->commit_n[i])
+          B200_CUDA(cudaMemcpyAsync(sg + off * g1b, d.commit_basis_exp_sigma[i].ptr, pk->commit_n[i] * g1b,
+                                    cudaMemcpyHostToDevice, s));
+        off += pk->commit_n[i];
+      }
+      cb->build_tables(in->tSigma, 1, sg, total_sigma, 0, s);
+      B200_CUDA(cudaStreamSynchronize(s));
+    }
     for (uint32_t i = 0; i < d.nb_commitments; i++) {
-      in->basis[i].reset(new DevBuf());
-      upload(*in->basis[i], d.commit_basis[i].ptr, pk->commit_n[i] * g1b, s);
-      if (pk->commit_n[i])
-        B200_CUDA(cudaMemcpyAsync(sg + off * g1b, d.commit_basis_exp_sigma[i].ptr, pk->commit_n[i] * g1b,
-                                  cudaMemcpyHostToDevice, s));
-      off += pk->commit_n[i];
+      in->tBasis[i].reset(new MsmBases());
+      put_tables(*in->tBasis[i], 1, d.commit_basis[i], g1b, nullptr, nullptr);
     }
     // ---- domain tables
     uint8_t* gens = (uint8_t*)in->gens.get(2 * frb);
@@ -230,11 +242,11 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
 
   // ---- s1: Ar, Bs1   s2: Bs (G2)
   B200_CUDA(cudaStreamWaitEvent(s1, S.ev[0], 0));
-  cb->msm(1, I.A.p, W, m + 4, o_ar, S.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapA.p);
-  cb->msm(1, I.B1.p, W, m + 4, o_bs1, S.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapB.p);
+  cb->msm(1, nullptr, W, m + 4, o_ar, S.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapA.p, &I.tA);
+  cb->msm(1, nullptr, W, m + 4, o_bs1, S.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapB.p, &I.tB1);
   B200_CUDA(cudaEventRecord(S.ev[1], s1));
   B200_CUDA(cudaStreamWaitEvent(s2, S.ev[0], 0));
-  cb->msm(2, I.B2.p, W, m + 4, o_bs2, S.ws[2], s2, 0, nullptr, (const uint32_t*)I.mapB.p);
+  cb->msm(2, nullptr, W, m + 4, o_bs2, S.ws[2], s2, 0, nullptr, (const uint32_t*)I.mapB.p, &I.tB2);
   B200_CUDA(cudaEventRecord(S.ev[2], s2));
 
   // ---- s0: quotient, Z and K MSMs, proof of knowledge
@@ -250,9 +262,9 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
     B200_CUDA(cudaMemcpyAsync(c, in.c.ptr, nc * frb, kind, s0));
   }
   cb->compute_h(I.dom, a, b, c, s0);
-  cb->msm(1, I.Z.p, a, nZ, o_z, S.ws[0], s0, 0, nullptr, nullptr);
-  cb->msm(1, I.K.p, W + nb_public * frb, m - nb_public + 4, o_k, S.ws[0], s0, 0, nullptr,
-          (const uint32_t*)I.mapK.p);
+  cb->msm(1, nullptr, a, nZ, o_z, S.ws[0], s0, 0, nullptr, nullptr, &I.tZ);
+  cb->msm(1, nullptr, W + nb_public * frb, m - nb_public + 4, o_k, S.ws[0], s0, 0, nullptr,
+          (const uint32_t*)I.mapK.p, &I.tK);
   bool have_pok = total_commit > 0 || !commit_n.empty();
   if (have_pok) {
     uint8_t* cv = (uint8_t*)S.cvals.p;
@@ -274,7 +286,7 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
       if (i >= 1) cb->scale_vec(cv + off * frb, S.chal.p, total_commit - off, s0);
       off += commit_n[i];
     }
-    cb->msm(1, I.sigma_all.p, cv, total_commit, o_pok, S.ws[0], s0, 0, nullptr, nullptr);
+    cb->msm(1, nullptr, cv, total_commit, o_pok, S.ws[0], s0, 0, nullptr, nullptr, &I.tSigma);
   }
   B200_CUDA(cudaStreamWaitEvent(s0, S.ev[1], 0));
   B200_CUDA(cudaStreamWaitEvent(s0, S.ev[2], 0));
@@ -316,7 +328,7 @@ void ProvingKeyDev::commit(uint32_t i, const b200_slice& values, void* out_affin
   uint8_t* cv = (uint8_t*)S.cvals.p;
   if (values.len) B200_CUDA(cudaMemcpyAsync(cv, values.ptr, values.len * frb, cudaMemcpyHostToDevice, s0));
   uint8_t* mo = (uint8_t*)S.msm_out.p;
-  cb->msm(1, I.basis[i]->p, cv, values.len, mo, S.ws[0], s0, 0, nullptr, nullptr);
+  cb->msm(1, nullptr, cv, values.len, mo, S.ws[0], s0, 0, nullptr, nullptr, I.tBasis[i].get());
   cb->to_affine(1, mo, S.out_aff.p, 1, s0);
   B200_CUDA(cudaMemcpyAsync(out_affine, S.out_aff.p, g1b, cudaMemcpyDeviceToHost, s0));
   B200_CUDA(cudaStreamSynchronize(s0));
@@ -345,10 +357,12 @@ std::unique_ptr<KzgSrsDev> KzgSrsDev::create(const uint8_t* g1_lagrange_compress
     const size_t g1b = cb->affine_bytes(1);
     DevBuf raw;
     upload(raw, g1_lagrange_compressed, (size_t)npoints * 48, in->st);
-    in->points.get((size_t)npoints * g1b);
+    DevBuf pts;
+    pts.get((size_t)npoints * g1b);
     uint32_t* err = (uint32_t*)in->err.get(4);
     B200_CUDA(cudaMemsetAsync(err, 0, 4, in->st));
-    cb->g1_decompress(raw.p, in->points.p, npoints, err, in->st);
+    cb->g1_decompress(raw.p, pts.p, npoints, err, in->st);
+    cb->build_tables(in->tables, 1, pts.p, npoints, 0, in->st);
     upload(in->brp, brp.data(), (size_t)npoints * 4, in->st);
     in->blob.get((size_t)npoints * 32);
     in->scalars.get((size_t)npoints * cb->fr_bytes());
@@ -384,7 +398,7 @@ void KzgSrsDev::blob_commit(const uint8_t* blob, uint8_t* commitment48, int devi
   B200_CUDA(cudaMemcpyAsync(I->blob.p, blob, (size_t)npoints * 32, cudaMemcpyHostToDevice, I->st));
   cb->blob_to_scalars(I->blob.p, I->scalars.p, npoints, err, I->st);
   uint8_t* o = (uint8_t*)I->out.p;
-  cb->msm(1, I->points.p, I->scalars.p, npoints, o, I->ws, I->st, 0, nullptr, (const uint32_t*)I->brp.p);
+  cb->msm(1, nullptr, I->scalars.p, npoints, o, I->ws, I->st, 0, nullptr, (const uint32_t*)I->brp.p, &I->tables);
   cb->to_affine(1, o, o + x1, 1, I->st);
   cb->g1_compress(o + x1, o + x1 + g1b, 1, I->st);
   uint32_t herr = 0;

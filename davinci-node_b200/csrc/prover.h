@@ -29,8 +29,11 @@ constexpr int kSlotsPerDevice = 2;
 // One copy of a proving key on one GPU.
 struct PkInstance {
   int device;
-  DevBuf A, B1, B2, K, Z, mapA, mapB, mapK, sigma_all, gens;
-  std::vector<std::unique_ptr<DevBuf>> basis;
+  // every base set lives as precomputed window tables (MsmBases, table mode): A||delta||alpha,
+  // B||delta||beta (G1 and G2), K||delta, Z, the concatenated sigma bases and each commitment basis
+  MsmBases tA, tB1, tB2, tK, tZ, tSigma;
+  std::vector<std::unique_ptr<MsmBases>> tBasis;
+  DevBuf mapA, mapB, mapK, gens;
   NttDomain dom;
   std::vector<std::unique_ptr<PkSlot>> slots;
   std::atomic<uint32_t> next_slot{0};
@@ -58,7 +61,8 @@ struct KzgSrsDev {
     int device = 0;
     std::mutex mu;
     cudaStream_t st = nullptr;
-    DevBuf points, brp, blob, scalars, out, err;
+    MsmBases tables;
+    DevBuf brp, blob, scalars, out, err;
     MsmWorkspace ws;
     ~Inst();
   };

@@ -61,6 +61,15 @@ B200_API int b200_msm_dev(int curve, int group, const void* d_points_affine, con
                  void* d_out_xyzz, int window_bits, void* cuda_stream);
 /* normalise `count` XYZZ points to affine on the device */
 B200_API int b200_to_affine_dev(int curve, int group, const void* d_xyzz, void* d_affine, uint32_t count, void* cuda_stream);
+/* Table mode: a base-point set registered once keeps its window multiples T_j[i] = 2^(c j) P_i resident
+ * in HBM; MSMs over it need no Horner pass and far fewer buckets (this is how the proving key and the
+ * KZG SRS are held; gnark re-reads pk.G1.A etc. on every proof instead).  d_index_map is optional:
+ * scalar i multiplies base map[i] (0xffffffff skips it). */
+B200_API int b200_bases_create_dev(int curve, int group, const void* d_points_affine, uint64_t n, int window_bits,
+                                   uint64_t* handle_out, void* cuda_stream);
+B200_API int b200_bases_release(uint64_t handle);
+B200_API int b200_msm_bases_dev(uint64_t handle, const void* d_scalars_mont, uint64_t n, const uint32_t* d_index_map,
+                                void* d_out_xyzz, void* cuda_stream);
 /* plan the MSM would use for (n, curve): out[0]=window bits c, [1]=windows, [2]=buckets/window,
  * [3]=task size, [4]=group size */
 B200_API int b200_msm_plan(int curve, uint64_t n, int window_bits, uint32_t out[5]);

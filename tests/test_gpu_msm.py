@@ -99,3 +99,45 @@ def test_msm_skewed_buckets_overflow_path(env, cname):
     assert gpu_msm_dev(capi, L, 1, pts, [k] * n, 8) == want
     sc = [1 if rnd.random() < 0.5 else (0 if rnd.random() < 0.5 else rnd.randrange(1 << 64)) for _ in range(n)]
     assert gpu_msm_dev(capi, L, 1, pts, sc, 0) == G.msm(pts, sc)
+
+
+@pytest.mark.parametrize("cname,group", [("bls12_377", 1), ("bls12_377", 2), ("bn254", 1), ("bw6_761", 1), ("bls12_381", 1)])
+def test_msm_table_mode(env, cname, group):
+    """Base set registered once (precomputed window multiples), with and without an index map,
+    several window widths: same affine result as the oracle's definition."""
+    import ctypes as C
+    from gpu_util import rand_points, to_dev, dev_empty, ptr, stream, sync
+    capi, layout = env
+    L = layout.Layout(cname)
+    cx = ocurve.ctx(cname)
+    G = cx.group(group)
+    rnd = random.Random(17 + group)
+    n = 260
+    pts = rand_points(cx, group, n, rnd)
+    pts[5] = None
+    sc = [rnd.randrange(cx.r) for _ in range(n)]
+    sc[0], sc[1], sc[2], sc[3] = 0, 1, cx.r - 1, rnd.randrange(1 << 64)
+    want = G.msm(pts, sc)
+    dp = to_dev(L.enc_affine(pts, group))
+    ds = to_dev(L.enc_fr(sc))
+    for c in (0, 5, 11):
+        h = C.c_uint64(0)
+        capi.check(capi.lib.b200_bases_create_dev(L.id, group, ptr(dp), n, c, C.byref(h), stream()))
+        try:
+            ox, oa = dev_empty(L.xyzz_bytes(group)), dev_empty(L.affine_bytes(group))
+            capi.check(capi.lib.b200_msm_bases_dev(h.value, ptr(ds), n, None, ptr(ox), stream()))
+            capi.check(capi.lib.b200_to_affine_dev(L.id, group, ptr(ox), ptr(oa), 1, stream()))
+            sync()
+            assert L.dec_affine(oa.cpu().numpy(), group)[0] == want, (cname, group, c)
+            # index map: reversed bases, one scalar skipped, fewer scalars than bases
+            k = n - 7
+            m = np.arange(n - 1, n - 1 - k, -1, dtype=np.uint32)
+            m[9] = 0xFFFFFFFF
+            dm = to_dev(m.view(np.uint8))
+            capi.check(capi.lib.b200_msm_bases_dev(h.value, ptr(ds), k, ptr(dm), ptr(ox), stream()))
+            capi.check(capi.lib.b200_to_affine_dev(L.id, group, ptr(ox), ptr(oa), 1, stream()))
+            sync()
+            want2 = G.msm([pts[n - 1 - i] for i in range(k) if i != 9], [sc[i] for i in range(k) if i != 9])
+            assert L.dec_affine(oa.cpu().numpy(), group)[0] == want2
+        finally:
+            capi.check(capi.lib.b200_bases_release(h.value))

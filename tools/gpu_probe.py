@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Ad-hoc GPU probe (not a test, not the bench): Montgomery-multiply issue-rate calibration and raw
 MSM timings on random data.  Writes gpurun_out/probe.json."""
+import ctypes as C
 import json
 import os
 import sys
@@ -68,8 +69,16 @@ def main():
                                                                      out.data_ptr(), 0, st)))
         rec = {"curve": L.name, "group": group, "log_n": lg, "ms": ms, "all_ms": all_ms, "plan": plan,
                "points_per_s": n / ms * 1e3}
+        # table mode (precomputed window multiples resident in HBM)
+        hb = C.c_uint64(0)
+        t0 = time.time()
+        capi.check(capi.lib.b200_bases_create_dev(cid, group, pts.data_ptr(), n, 0, C.byref(hb), st))
+        rec["table_build_s"] = time.time() - t0
+        tms, _ = timed(lambda: capi.check(capi.lib.b200_msm_bases_dev(hb.value, sc.data_ptr(), n, None, out.data_ptr(), st)))
+        rec["table_ms"] = tms
+        capi.check(capi.lib.b200_bases_release(hb.value))
         res["msm"].append(rec)
-        print("msm", rec, flush=True)
+        print("msm", {k: rec[k] for k in ("curve", "group", "log_n", "ms", "table_ms", "table_build_s")}, flush=True)
         del pts, sc
         torch.cuda.empty_cache()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
