@@ -308,7 +308,9 @@ def main():
     outx = torch.zeros(L.xyzz_bytes(2), dtype=torch.uint8, device="cuda")
     # uniform full-width scalars (the quotient's a-vector): the SURVEY 8d work formula is exact for them,
     # whereas the witness-like wire vector skips ~60% of the points and would flatter the fraction
-    msm_dev = lambda: capi.check(lib.b200_msm_dev(L.id, 2, b2.data_ptr(), sol["a_dev"].data_ptr(), nB, outx.data_ptr(), 0, st))
+    hb = C.c_uint64(0)
+    capi.check(lib.b200_bases_create_dev(L.id, 2, b2.data_ptr(), nB, 0, C.byref(hb), st))   # table mode, as the key is held
+    msm_dev = lambda: capi.check(lib.b200_msm_bases_dev(hb.value, sol["a_dev"].data_ptr(), nB, None, outx.data_ptr(), st))
     msm_dev()
     torch.cuda.synchronize()
     capi.check(lib.b200_profile_enable(1))

@@ -252,14 +252,14 @@ k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restric
   uint32_t mine = cnt;
   if (cnt > pl.task) {
     mine = pl.task;
-    uint32_t extra = (cnt - pl.task + kOvfTask - 1) / kOvfTask;
+    uint32_t extra = (cnt - pl.task + pl.ovf_task - 1) / pl.ovf_task;
     uint32_t first = atomicAdd(&ctr->ntasks, extra);
     if (first + extra <= pl.max_ovf) {
       uint32_t ob = atomicAdd(&ctr->nbuckets, 1u);
       obuckets[ob] = OvfBucket{gb, first, extra, 0};
       uint32_t s = start + pl.task, left = cnt - pl.task;
       for (uint32_t k = 0; k < extra; k++) {
-        uint32_t l = left < kOvfTask ? left : kOvfTask;
+        uint32_t l = left < pl.ovf_task ? left : pl.ovf_task;
         tasks[first + k] = OvfTask{gb, s, l, 0};
         s += l;
         left -= l;

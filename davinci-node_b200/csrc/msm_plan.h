@@ -21,6 +21,7 @@ struct MsmPlan {
   int bwin;            // bucket windows: nwin (windowed) or 1 (table mode)
   uint32_t nb;         // buckets per bucket window = 2^(c-1)
   uint32_t task;       // max points a single thread accumulates for one bucket
+  uint32_t ovf_task;   // points per overflow task (the remainder of an oversized bucket)
   uint32_t group;      // buckets per running-sum group
   uint32_t max_ovf;    // capacity of the overflow task list
   uint64_t npts;       // table mode: points per table (index of digit window w is w*npts + i)
@@ -31,6 +32,15 @@ inline int msm_nwin(int scalar_bits, int c) { return (scalar_bits + 1 + c - 1) /
 
 // window width for a table-mode base set of npts points (fixed when the tables are built)
 inline int msm_table_window(uint64_t npts, int scalar_bits) {
+  // small base sets (e.g. the 4096-point KZG SRS) are latency-bound: every sequential point addition
+  // costs ~8 us on an almost empty GPU, so take the smallest window that leaves <= ~4 points per bucket
+  if (npts <= (1u << 16)) {
+    for (int c = 8; c <= 16; c++) {
+      double nb = std::ldexp(1.0, c - 1);
+      if ((double)npts * msm_nwin(scalar_bits, c) / nb <= 4.0) return c;
+    }
+    return 16;
+  }
   int best_c = 4;
   double best = 1e300;
   for (int c = 4; c <= 22; c++) {
@@ -51,12 +61,16 @@ inline void msm_plan_finish(MsmPlan& pl) {
   const uint64_t adds = pl.n * (uint64_t)pl.nwin;
   const uint64_t total_b = (uint64_t)pl.bwin * pl.nb;
   uint64_t avg = adds / total_b + 1;
-  pl.task = (uint32_t)std::max<uint64_t>(256, 8 * avg);
+  // large MSMs: size-sorted scheduling hides long buckets, keep overflow rare.  small MSMs: the longest
+  // per-thread chain IS the latency, so cap it hard and split the rest into short parallel tasks.
+  const bool small = adds < (1u << 21);
+  pl.task = small ? (uint32_t)std::max<uint64_t>(16, 4 * avg) : (uint32_t)std::max<uint64_t>(256, 8 * avg);
+  pl.ovf_task = small ? (uint32_t)std::min<uint64_t>(kOvfTaskPoints, std::max<uint64_t>(16, 2 * avg)) : kOvfTaskPoints;
   uint32_t g = 1;
   while (g * 2 <= 64 && (uint64_t)g * 2 * 16384 <= total_b) g *= 2;
   if (g < 4) g = std::min<uint32_t>(4, pl.nb);
   pl.group = std::min<uint32_t>(g, pl.nb);
-  pl.max_ovf = (uint32_t)(adds / kOvfTaskPoints + 1);
+  pl.max_ovf = (uint32_t)(adds / pl.ovf_task + 1);
   pl.stride = pl.bwin == 1 ? adds : pl.n;
 }
 
