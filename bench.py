@@ -321,6 +321,7 @@ def main():
     cnt = (C.c_uint64 * 5)()
     capi.check(lib.b200_profile_collect(ms, cnt))
     g2_total_ms, g2_acc_ms = ms[4] / max(cnt[4], 1), ms[1] / max(cnt[1], 1)
+    capi.check(lib.b200_bases_release(hb.value))
     del b2
     # NTT passes alone (quotient on resident buffers)
     dom = C.c_uint64(0)
