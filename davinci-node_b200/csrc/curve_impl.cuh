@@ -246,7 +246,8 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   Pt* windows = (Pt*)ws.windows.get((uint64_t)pl.bwin * sizeof(Pt));
   OvfCounters* ctr = (OvfCounters*)ws.ctr.get(sizeof(OvfCounters));
   uint32_t* perm = (uint32_t*)ws.perm.get(total_b * 4);
-  uint32_t* bins = (uint32_t*)ws.bins.get(2 * kSizeBins * 4);   // [bins | cursor]
+  uint32_t* bins = (uint32_t*)ws.bins.get((2 * kSizeBins + pl.bwin) * 4);   // [bins | cursor | window totals]
+  uint32_t* totals = bins + 2 * kSizeBins;
 
   B200_CUDA(cudaMemsetAsync(hist, 0, total_b * 4, s));
   B200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(OvfCounters), s));
@@ -256,7 +257,7 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   const unsigned sblocks = (unsigned)((n + 255) / 256);
   const int tok_total = prof_begin(GROUP == 2 ? PROF_MSM_TOTAL_G2 : PROF_MSM_TOTAL_G1, s);
   k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, d_index_map);
-  k_msm_scan<<<pl.bwin, 1024, 0, s>>>(hist, pl, off, cur);
+  k_msm_scan<<<pl.bwin, 1024, 0, s>>>(hist, pl, off, cur, totals);
   k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, d_index_map);
   // size-sorted bucket schedule
   const unsigned szblocks = (unsigned)((total_b + kSizeThreads * kSizePerThread - 1) / (kSizeThreads * kSizePerThread));
@@ -264,8 +265,8 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   k_msm_size_scan<<<1, kSizeBins, 0, s>>>(bins, bins + kSizeBins);
   k_msm_size_scatter<<<szblocks, kSizeThreads, 0, s>>>(off, cur, total_b, bins + kSizeBins, perm);
   const int tok_acc = prof_begin(GROUP == 2 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1, s);
-  k_msm_accumulate<F><<<(unsigned)((total_b + 127) / 128), 128, 0, s>>>(pts, sorted, off, cur, perm, pl, buckets,
-                                                                         tasks, obuckets, ctr);
+  k_msm_accumulate<F><<<(unsigned)((total_b + 127) / 128), 128, 0, s>>>(pts, sorted, off, cur, perm, totals, pl,
+                                                                         buckets, tasks, obuckets, ctr);
   prof_end(tok_acc, s);
   // oversized buckets (skewed scalar distributions, e.g. the many 1-valued witness wires)
   unsigned ovf_blocks = (unsigned)std::min<uint64_t>((pl.max_ovf + 127) / 128, 148 * 8);

@@ -62,9 +62,13 @@ __global__ void k_msm_hist(const typename Fr::El* __restrict__ scalars, MsmPlan 
   for_each_digit<Fr>(s, pl, [&](int w, uint32_t b, bool) { atomicAdd(&hist[(table ? 0 : (uint64_t)w * pl.nb) + b], 1u); });
 }
 
-// one block per window: exclusive scan of hist -> off (start offsets) and cur (running cursors)
-static __global__ void k_msm_scan(const uint32_t* __restrict__ hist, MsmPlan pl, uint32_t* __restrict__ off,
-                           uint32_t* __restrict__ cur) {
+// one block per bucket window: exclusive scan of hist -> off (start offsets) and cur (running cursors);
+// also totals[w] = number of (point, digit) entries of the window.  Each thread owns kScanItems
+// consecutive buckets per sweep, so 2^19 buckets take 32 sweeps instead of 512.
+constexpr int kScanItems = 16;
+static __global__ void __launch_bounds__(1024)
+k_msm_scan(const uint32_t* __restrict__ hist, MsmPlan pl, uint32_t* __restrict__ off, uint32_t* __restrict__ cur,
+           uint32_t* __restrict__ totals) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
   const uint32_t* h = hist + (uint64_t)blockIdx.x * pl.nb;
@@ -73,10 +77,17 @@ static __global__ void k_msm_scan(const uint32_t* __restrict__ hist, MsmPlan pl,
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (uint32_t base = 0; base < pl.nb; base += blockDim.x) {
-    uint32_t idx = base + threadIdx.x;
-    uint32_t v = idx < pl.nb ? h[idx] : 0;
-    uint32_t x = v;
+  const uint32_t per_sweep = blockDim.x * kScanItems;
+  for (uint32_t base = 0; base < pl.nb; base += per_sweep) {
+    uint32_t first = base + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+      v[k] = first + k < pl.nb ? h[first + k] : 0;
+      sum += v[k];
+    }
+    uint32_t x = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
@@ -94,15 +105,20 @@ static __global__ void k_msm_scan(const uint32_t* __restrict__ hist, MsmPlan pl,
       warp_sums[lane] = ws;   // inclusive
     }
     __syncthreads();
-    uint32_t prefix = carry_s + (wid ? warp_sums[wid - 1] : 0) + (x - v);
-    if (idx < pl.nb) {
-      o[idx] = prefix;
-      c[idx] = prefix;
+    uint32_t prefix = carry_s + (wid ? warp_sums[wid - 1] : 0) + (x - sum);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+      if (first + k < pl.nb) {
+        o[first + k] = prefix;
+        c[first + k] = prefix;
+      }
+      prefix += v[k];
     }
     __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = prefix + v;
+    if (threadIdx.x == blockDim.x - 1) carry_s = prefix;
     __syncthreads();
   }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
 }
 
 template <class Fr>
@@ -242,22 +258,27 @@ template <class F>
 __global__ void __launch_bounds__(128, B200_ACC_MIN_BLOCKS)
 k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted,
                  const uint32_t* __restrict__ off, const uint32_t* __restrict__ end,
-                 const uint32_t* __restrict__ perm, MsmPlan pl, XYZZ<F>* __restrict__ buckets,
-                 OvfTask* __restrict__ tasks, OvfBucket* __restrict__ obuckets, OvfCounters* __restrict__ ctr) {
+                 const uint32_t* __restrict__ perm, const uint32_t* __restrict__ totals, MsmPlan pl,
+                 XYZZ<F>* __restrict__ buckets, OvfTask* __restrict__ tasks, OvfBucket* __restrict__ obuckets,
+                 OvfCounters* __restrict__ ctr) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (uint64_t)pl.bwin * pl.nb) return;
   const uint32_t gb = perm[t];
   uint32_t w = gb / pl.nb;
   uint32_t start = off[gb], cnt = end[gb] - start;
   uint32_t mine = cnt;
-  if (cnt > pl.task) {
-    mine = pl.task;
-    uint32_t extra = (cnt - pl.task + pl.ovf_task - 1) / pl.ovf_task;
+  // the cap follows the ACTUAL mean bucket load of this window (sparse witness vectors fill far fewer
+  // digits than n * nwin): a single thread's chain of additions is pure latency (~8 us each)
+  uint32_t task = 4u * (totals[w] / pl.nb + 1u);
+  task = task < pl.task_min ? pl.task_min : (task > pl.task ? pl.task : task);
+  if (cnt > task) {
+    mine = task;
+    uint32_t extra = (cnt - task + pl.ovf_task - 1) / pl.ovf_task;
     uint32_t first = atomicAdd(&ctr->ntasks, extra);
     if (first + extra <= pl.max_ovf) {
       uint32_t ob = atomicAdd(&ctr->nbuckets, 1u);
       obuckets[ob] = OvfBucket{gb, first, extra, 0};
-      uint32_t s = start + pl.task, left = cnt - pl.task;
+      uint32_t s = start + task, left = cnt - task;
       for (uint32_t k = 0; k < extra; k++) {
         uint32_t l = left < pl.ovf_task ? left : pl.ovf_task;
         tasks[first + k] = OvfTask{gb, s, l, 0};

@@ -21,6 +21,7 @@ struct MsmPlan {
   int bwin;            // bucket windows: nwin (windowed) or 1 (table mode)
   uint32_t nb;         // buckets per bucket window = 2^(c-1)
   uint32_t task;       // max points a single thread accumulates for one bucket
+  uint32_t task_min;   // lower bound of the load-adaptive cap
   uint32_t ovf_task;   // points per overflow task (the remainder of an oversized bucket)
   uint32_t group;      // buckets per running-sum group
   uint32_t max_ovf;    // capacity of the overflow task list
@@ -64,13 +65,17 @@ inline void msm_plan_finish(MsmPlan& pl) {
   // large MSMs: size-sorted scheduling hides long buckets, keep overflow rare.  small MSMs: the longest
   // per-thread chain IS the latency, so cap it hard and split the rest into short parallel tasks.
   const bool small = adds < (1u << 21);
-  pl.task = small ? (uint32_t)std::max<uint64_t>(16, 4 * avg) : (uint32_t)std::max<uint64_t>(256, 8 * avg);
+  // `task` is the upper cap; the kernel lowers it to 4x the measured mean load (never below task_min)
+  pl.task = small ? (uint32_t)std::max<uint64_t>(16, 4 * avg) : (uint32_t)std::max<uint64_t>(256, 4 * avg);
+  pl.task_min = small ? 16 : 64;
   pl.ovf_task = small ? (uint32_t)std::min<uint64_t>(kOvfTaskPoints, std::max<uint64_t>(16, 2 * avg)) : kOvfTaskPoints;
+  // running-sum groups: short groups keep the (latency-bound) bucket reduction shallow
   uint32_t g = 1;
-  while (g * 2 <= 64 && (uint64_t)g * 2 * 16384 <= total_b) g *= 2;
+  while (g * 2 <= 8 && (uint64_t)g * 2 * 16384 <= total_b) g *= 2;
   if (g < 4) g = std::min<uint32_t>(4, pl.nb);
   pl.group = std::min<uint32_t>(g, pl.nb);
-  pl.max_ovf = (uint32_t)(adds / pl.ovf_task + 1);
+  // every overflowing bucket holds > task_min points and every overflow task but the last is full
+  pl.max_ovf = (uint32_t)(adds / pl.ovf_task + adds / pl.task_min + 2);
   pl.stride = pl.bwin == 1 ? adds : pl.n;
 }
 
