@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--logn", type=int, default=22)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="proofs per step per GPU")
-    ap.add_argument("--inflight", type=int, default=2, help="proofs in flight per GPU (host threads)")
+    ap.add_argument("--inflight", type=int, default=4, help="proofs in flight per GPU (host threads, <= 4 slots)")
     ap.add_argument("--cpu-logn", type=int, default=17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -354,7 +354,11 @@ def main():
     roofline = {"bound": "imad", "kernel": "G2 MSM, %d points, uniform 253-bit scalars (k_msm_accumulate<Fp2> = %.0f%% of it)" % (nB, 100 * g2_acc_ms / g2_total_ms),
                 "achieved": achieved / 1e12, "peak": peak_meas / 1e12, "unit": "T wide-MAC/s (32x32->64 IMAD.WIDE)",
                 "frac": achieved / peak_meas, "peak_source": "measured in this run (b200_calib_mul_dev); nominal 148*64*f = %.2f" % (peak_nominal / 1e12),
-                "frac_of_nominal": achieved / peak_nominal, "traffic": None,
+                "frac_of_nominal": achieved / peak_nominal,
+                # dram__bytes_read+write of k_msm_accumulate<Fp2> from the committed ncu capture at 2^21 points
+                # (profiles/r1_ncu_msm_accumulate_g2.md: 10.38 GB + 17.51 GB), scaled to this launch's point count
+                "traffic": (10.38e9 + 17.51e9) * nB / float(1 << 21),
+                "traffic_note": "algorithmic point bytes = adds* x 192 B; the excess is Fp2 accumulator spill traffic",
                 "launch_ms": g2_total_ms, "algorithmic_macs_per_launch": g2_alg}
     ntt_bytes = 2 * wl.n * L.fr_bytes
     roofline_ntt = {"bound": "hbm", "kernel": "k_ntt_pass (one 2^%d transform = %d passes)" % (args.logn, ntt_passes),

@@ -269,7 +269,7 @@ k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restric
   uint32_t mine = cnt;
   // the cap follows the ACTUAL mean bucket load of this window (sparse witness vectors fill far fewer
   // digits than n * nwin): a single thread's chain of additions is pure latency (~8 us each)
-  uint32_t task = 4u * (totals[w] / pl.nb + 1u);
+  uint32_t task = 8u * (totals[w] / pl.nb + 1u);
   task = task < pl.task_min ? pl.task_min : (task > pl.task ? pl.task : task);
   if (cnt > task) {
     mine = task;

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -66,12 +67,16 @@ inline void msm_plan_finish(MsmPlan& pl) {
   // per-thread chain IS the latency, so cap it hard and split the rest into short parallel tasks.
   const bool small = adds < (1u << 21);
   // `task` is the upper cap; the kernel lowers it to 4x the measured mean load (never below task_min)
-  pl.task = small ? (uint32_t)std::max<uint64_t>(16, 4 * avg) : (uint32_t)std::max<uint64_t>(256, 4 * avg);
+  pl.task = small ? (uint32_t)std::max<uint64_t>(16, 4 * avg) : (uint32_t)std::max<uint64_t>(256, 8 * avg);
   pl.task_min = small ? 16 : 64;
   pl.ovf_task = small ? (uint32_t)std::min<uint64_t>(kOvfTaskPoints, std::max<uint64_t>(16, 2 * avg)) : kOvfTaskPoints;
   // running-sum groups: short groups keep the (latency-bound) bucket reduction shallow
   uint32_t g = 1;
-  while (g * 2 <= 8 && (uint64_t)g * 2 * 16384 <= total_b) g *= 2;
+  static const uint32_t gmax = [] {
+    const char* e = std::getenv("B200_MSM_GROUP_MAX");   // tuning knob (default 32)
+    return e ? (uint32_t)std::atoi(e) : 32u;
+  }();
+  while (g * 2 <= gmax && (uint64_t)g * 2 * 16384 <= total_b) g *= 2;
   if (g < 4) g = std::min<uint32_t>(4, pl.nb);
   pl.group = std::min<uint32_t>(g, pl.nb);
   // every overflowing bucket holds > task_min points and every overflow task but the last is full

@@ -24,7 +24,7 @@ struct PkSlot {
   ~PkSlot();
 };
 
-constexpr int kSlotsPerDevice = 2;
+constexpr int kSlotsPerDevice = 4;
 
 // One copy of a proving key on one GPU.
 struct PkInstance {
