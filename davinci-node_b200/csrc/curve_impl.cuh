@@ -265,7 +265,7 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   k_msm_size_scan<<<1, kSizeBins, 0, s>>>(bins, bins + kSizeBins);
   k_msm_size_scatter<<<szblocks, kSizeThreads, 0, s>>>(off, cur, total_b, bins + kSizeBins, perm);
   const int tok_acc = prof_begin(GROUP == 2 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1, s);
-  k_msm_accumulate<F><<<(unsigned)((total_b + 127) / 128), 128, 0, s>>>(pts, sorted, off, cur, perm, totals, pl,
+  k_msm_accumulate<F><<<(unsigned)((total_b + B200_ACC_THREADS - 1) / B200_ACC_THREADS), B200_ACC_THREADS, 0, s>>>(pts, sorted, off, cur, perm, totals, pl,
                                                                          buckets, tasks, obuckets, ctr);
   prof_end(tok_acc, s);
   // oversized buckets (skewed scalar distributions, e.g. the many 1-valued witness wires)

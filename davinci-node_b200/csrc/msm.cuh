@@ -255,7 +255,10 @@ template <class F>
 #ifndef B200_ACC_MIN_BLOCKS
 #define B200_ACC_MIN_BLOCKS 3
 #endif
-__global__ void __launch_bounds__(128, B200_ACC_MIN_BLOCKS)
+#ifndef B200_ACC_THREADS
+#define B200_ACC_THREADS 128
+#endif
+__global__ void __launch_bounds__(B200_ACC_THREADS, B200_ACC_MIN_BLOCKS)
 k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted,
                  const uint32_t* __restrict__ off, const uint32_t* __restrict__ end,
                  const uint32_t* __restrict__ perm, const uint32_t* __restrict__ totals, MsmPlan pl,

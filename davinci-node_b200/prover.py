@@ -26,6 +26,7 @@ import numpy as np
 from . import capi
 from .gnark_types import ConstraintSystem, Proof, ProvingKey, Witness
 from .layout import Layout
+from .setup import Setup, SetSetupRandomness, VerifyingKey  # noqa: F401  (prover/setup.go:15)
 
 # env GPU_PROVER, read at import like the reference's init() (prover/config.go:18-26)
 UseGPUProver = os.environ.get("GPU_PROVER", "true").lower() in ("1", "true", "yes")

@@ -90,3 +90,47 @@ def test_cpu_prover_is_absent(env):
         prover.CPUProver(1, None, None, None)
     with pytest.raises(prover.ProverError):
         prover.CPUProverWithWitness(1, None, None, None)
+
+
+@pytest.mark.parametrize("cname", ["bn254", "bls12_377"])
+def test_setup_mirror_matches_oracle_and_proves(env, cname):
+    """prover.Setup mirror (prover/setup.go:15): with the toxic waste pinned the GPU-built key equals
+    the oracle's key point for point, and a proof made with it satisfies the verifier equation."""
+    from oracle_bridge import ccs_from_oracle, pk_from_oracle
+    capi, layout, prover, T = env
+    cx = OC.ctx(cname)
+    q = cx.r
+    L = layout.Layout(cname)
+    rnd = random.Random(99)
+    cs, W0 = OG.synthetic_circuit(33, 4, q, seed=5, n_commit=1, n_private_committed=3)
+    tox = OG.Toxic(*(rnd.randrange(1, q) for _ in range(5)), sigmas=[rnd.randrange(1, q)])
+    opk, ex = OG.setup(cs, cx, tox)
+    want = pk_from_oracle(opk, L.id)
+    ccs = ccs_from_oracle(cs, L.id)
+    prover.SetSetupRandomness(lambda cid, k: dict(tau=tox.tau, alpha=tox.alpha, beta=tox.beta, gamma=tox.gamma,
+                                                  delta=tox.delta, sigmas=tox.sigmas))
+    try:
+        pk, vk = prover.Setup(ccs)
+    finally:
+        prover.SetSetupRandomness(None)
+    for name in ("g1_alpha", "g1_beta", "g1_delta", "g1_A", "g1_B", "g1_Z", "g1_K", "g2_beta", "g2_delta", "g2_B",
+                 "infinity_a", "infinity_b", "domain_generator", "domain_coset_gen"):
+        assert np.array_equal(getattr(pk, name), getattr(want, name)), name
+    assert np.array_equal(pk.commitment_keys[0]["Basis"], want.commitment_keys[0]["Basis"])
+    assert np.array_equal(pk.commitment_keys[0]["BasisExpSigma"], want.commitment_keys[0]["BasisExpSigma"])
+    assert L.dec_affine(vk.g1_K, 1) == [cx.G1.mul(cx.g1, k) for k in ex["vk_K"]]
+    assert L.dec_affine(vk.g2_gamma, 2)[0] == cx.G2.mul(cx.g2, tox.gamma)
+    # prove with the GPU-built key
+    w = T.Witness(L.id, W0[1:cs.nb_public], W0[cs.nb_public:cs.nb_public + ccs.nb_secret])
+    r, s = rnd.randrange(q), rnd.randrange(q)
+    prover.SetRandomness(lambda cid: (r, s))
+    try:
+        proof = prover.ProveWithWitness(L.id, ccs, pk, w)
+        sol = ccs.solve(w, lambda i, v: proof.Commitments[i])
+        A, B, Cx = OG.proof_exponents(cs, ex, tox, sol.values, r, s, q)
+        got = proof.points()
+        assert got["Ar"] == cx.G1.mul(cx.g1, A) and got["Krs"] == cx.G1.mul(cx.g1, Cx)
+        assert OG.verify_exponent(cs, ex, tox, sol.values, A, B, Cx, q)
+    finally:
+        prover.SetRandomness(None)
+        prover.release_proving_key(pk)
