@@ -182,6 +182,42 @@ __device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const Affine<F>* __
   }
 }
 
+// Lock-step variant: every warp of the block runs the same trip count and meets at a barrier each
+// iteration, so the (64 KB, larger than the instruction cache) loop body is streamed once per SM and
+// iteration instead of once per warp.  Buckets of a block have (almost) equal sizes thanks to the
+// size-sorted schedule, so the padding iterations are few.
+template <class F>
+__device__ __forceinline__ void accumulate_run_lockstep(XYZZ<F>& acc, const Affine<F>* __restrict__ points,
+                                                        const uint32_t* __restrict__ idx, uint32_t len) {
+  using E = EC<F>;
+  __shared__ uint32_t s_trips;
+  E::set_inf(acc);
+  if (threadIdx.x == 0) s_trips = 0;
+  __syncthreads();
+  if (len) atomicMax(&s_trips, len);
+  __syncthreads();
+  const uint32_t trips = s_trips;
+  uint32_t e = 0;
+  Affine<F> nxt;
+  if (len) {
+    e = idx[0];
+    load16(nxt, points + (e & 0x7fffffffu));
+  }
+  for (uint32_t k = 0; k < trips; k++) {
+    __syncthreads();
+    if (k < len) {
+      Affine<F> cur = nxt;
+      bool neg = e >> 31;
+      if (k + 1 < len) {
+        e = idx[k + 1];
+        load16(nxt, points + (e & 0x7fffffffu));
+      }
+      if (neg) E::neg(cur);
+      E::madd(acc, cur);
+    }
+  }
+}
+
 // ---- schedule: counting sort of the buckets by (clamped) size, largest first, so that the 32
 // buckets of a warp have equal trip counts (no divergence) and the heavy buckets start first (no tail)
 constexpr int kSizeBins = 1024;
@@ -252,6 +288,9 @@ k_msm_size_scatter(const uint32_t* __restrict__ off, const uint32_t* __restrict_
 constexpr uint32_t kOvfTask = kOvfTaskPoints;
 
 template <class F>
+#ifndef B200_ACC_NO_LOCKSTEP
+#define B200_ACC_LOCKSTEP 1   // measured: -5% (G1) / -8% (G2) accumulate time at 128 threads, 3 blocks per SM
+#endif
 #ifndef B200_ACC_MIN_BLOCKS
 #define B200_ACC_MIN_BLOCKS 3
 #endif
@@ -265,10 +304,13 @@ k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restric
                  XYZZ<F>* __restrict__ buckets, OvfTask* __restrict__ tasks, OvfBucket* __restrict__ obuckets,
                  OvfCounters* __restrict__ ctr) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint64_t)pl.bwin * pl.nb) return;
-  const uint32_t gb = perm[t];
+  const bool valid = t < (uint64_t)pl.bwin * pl.nb;
+#ifndef B200_ACC_LOCKSTEP
+  if (!valid) return;
+#endif
+  const uint32_t gb = valid ? perm[t] : 0;
   uint32_t w = gb / pl.nb;
-  uint32_t start = off[gb], cnt = end[gb] - start;
+  uint32_t start = valid ? off[gb] : 0, cnt = valid ? end[gb] - start : 0;
   uint32_t mine = cnt;
   // the cap follows the ACTUAL mean bucket load of this window (sparse witness vectors fill far fewer
   // digits than n * nwin): a single thread's chain of additions is pure latency (~8 us each)
@@ -293,8 +335,13 @@ k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restric
     }
   }
   XYZZ<F> acc;
+#ifdef B200_ACC_LOCKSTEP
+  accumulate_run_lockstep<F>(acc, points, sorted + (uint64_t)w * pl.stride + start, mine);
+  if (valid) store16(buckets + gb, acc);
+#else
   accumulate_run<F>(acc, points, sorted + (uint64_t)w * pl.stride + start, mine);
   store16(buckets + gb, acc);
+#endif
 }
 
 template <class F>
