@@ -54,13 +54,14 @@ def expected_exponents(wl, sol, r, s):
 
 
 @pytest.mark.parametrize("cname,logn,mix", [("bls12_377", 14, "witness"), ("bls12_377", 17, "witness"),
-                                            ("bn254", 15, "uniform"), ("bw6_761", 12, "witness")])
+                                            ("bn254", 15, "uniform"), ("bw6_761", 12, "witness"),
+                                            ("bls12_377", 22, "witness")])     # BASELINE.json's full size (~40 s)
 def test_structured_key_closed_form(cname, logn, mix):
     import torch
     from davinci_node_b200 import capi, prover, synthetic
     capi.init()
-    if os.environ.get("B200_FULLSIZE") and cname == "bls12_377" and logn == 17:
-        logn = 22
+    if logn >= 20 and os.environ.get("B200_SKIP_FULLSIZE"):
+        pytest.skip("full-size case disabled by B200_SKIP_FULLSIZE")
     cx = OC.ctx(cname)
     wl = synthetic.SyntheticWorkload(cname, logn, seed=logn)
     h = wl.register()
