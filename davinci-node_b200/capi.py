@@ -39,6 +39,7 @@ class PkDesc(C.Structure):
         ("infinity_a", Slice), ("infinity_b", Slice),
         ("nb_wires", _u64), ("nb_public", _u64), ("krs_skip", Slice),
         ("nb_commitments", _u32), ("commit_basis", C.POINTER(Slice)), ("commit_basis_exp_sigma", C.POINTER(Slice)),
+        ("z_offset", _u64),
     ]
 
 
@@ -71,6 +72,8 @@ _PROTOS = {
     "b200_launch_count": (_u64, []),
     "b200_profile_enable": (_i, [_i]),
     "b200_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(_u64)]),
+    "b200_prove_partial_dev": (_i, [_u64, C.POINTER(ProveIn), _vp, _i]),
+    "b200_assemble_dev": (_i, [_i, _vp, _u32, _vp, _vp, _i, _vp, _vp]),
     "b200_kzg_srs_register": (_i, [_vp, _u32, C.POINTER(_u64)]),
     "b200_kzg_srs_release": (_i, [_u64]),
     "b200_blob_commit": (_i, [_u64, _vp, _vp, _i]),

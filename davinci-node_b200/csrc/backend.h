@@ -141,6 +141,8 @@ struct CurveBackend {
   // --- point helpers
   virtual void to_affine(int group, const void* d_xyzz, void* d_affine, uint32_t count, cudaStream_t s) = 0;
   // affine(sum of count XYZZ points): combine of range-split MSM partials
+  // range-split prove: per-slot sums of nparts sets of [5 G1 XYZZ | 1 G2 XYZZ]
+  virtual void sum_sets(const void* d_partials, uint32_t nparts, void* d_sums, cudaStream_t s) = 0;
   virtual void sum_partials(int group, const void* d_xyzz, uint32_t count, void* d_affine, cudaStream_t s) = 0;
   // out = sum_i [k_i] P_i  (tiny, single thread): used for the alpha/beta/delta terms of the proof
   // --- debug / parity entry points (element-wise, device pointers)

@@ -359,6 +359,44 @@ int b200_prove_dev(uint64_t h, const b200_prove_in* in, const b200_proof_out* ou
   });
 }
 
+int b200_prove_partial_dev(uint64_t h, const b200_prove_in* in, void* d_partials_out, int device) {
+  return guarded([&] {
+    if (!in || !d_partials_out) throw std::runtime_error("null argument");
+    b200_proof_out none{};
+    find_pk(h)->prove(*in, none, device, true, d_partials_out);
+  });
+}
+
+int b200_assemble_dev(int curve_id, const void* d_partials, uint32_t nparts, const void* d_r, const void* d_s,
+                      int have_pok, void* d_out, void* stream) {
+  return guarded([&] {
+    if (!d_partials || !nparts || !d_r || !d_s || !d_out) throw std::runtime_error("null argument");
+    CurveBackend& cb = curve(curve_id);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t x1 = cb.xyzz_bytes(1), x2 = cb.xyzz_bytes(2), g1b = cb.affine_bytes(1), frb = cb.fr_bytes();
+    ScopedDev sums(5 * x1 + x2), rs(4 * frb), tmp(2 * x1);
+    cb.sum_sets(d_partials, nparts, sums.p, s);
+    cb.prep_rs(d_r, d_s, rs.p, s);
+    uint8_t* sm = (uint8_t*)sums.p;
+    uint8_t* o = (uint8_t*)d_out;
+    AssembleArgs aa{};
+    aa.ar_msm = sm;
+    aa.bs1_msm = sm + x1;
+    aa.k_msm = sm + 2 * x1;
+    aa.z_msm = sm + 3 * x1;
+    aa.pok_msm = have_pok ? sm + 4 * x1 : nullptr;
+    aa.bs2_msm = sm + 5 * x1;
+    aa.rs = rs.p;
+    aa.tmp = tmp.p;
+    aa.out_ar = o;
+    aa.out_krs = o + g1b;
+    aa.out_pok = o + 2 * g1b;
+    aa.out_bs = o + 3 * g1b;
+    cb.assemble(aa, s);
+    B200_CUDA(cudaStreamSynchronize(s));   // scratch is scoped to this call
+  });
+}
+
 // ---------------------------------------------------------------------------------- KZG
 int b200_kzg_srs_register(const uint8_t* g1_lagrange, uint32_t npoints, uint64_t* handle_out) {
   return guarded([&] {

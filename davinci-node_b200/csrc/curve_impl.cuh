@@ -195,6 +195,31 @@ __global__ void k_assemble_out(const XYZZ<F1>* ar, const XYZZ<F2>* bs2, const XY
   }
 }
 
+// sums[j] = sum over parts of partials[part][j]; slots 0..4 are G1 XYZZ, slot 5 is G2 XYZZ (range-split prove)
+template <class F1, class F2>
+__global__ void k_sum_sets(const uint8_t* __restrict__ partials, uint32_t nparts, uint8_t* __restrict__ sums) {
+  const size_t x1 = sizeof(XYZZ<F1>), x2 = sizeof(XYZZ<F2>), set = 5 * x1 + x2;
+  if (threadIdx.x) return;
+  const int j = blockIdx.x;
+  if (j < 5) {
+    XYZZ<F1> acc;
+    EC<F1>::set_inf(acc);
+    for (uint32_t p = 0; p < nparts; p++) {
+      XYZZ<F1> v = *reinterpret_cast<const XYZZ<F1>*>(partials + p * set + j * x1);
+      EC<F1>::add(acc, v);
+    }
+    *reinterpret_cast<XYZZ<F1>*>(sums + j * x1) = acc;
+  } else {
+    XYZZ<F2> acc;
+    EC<F2>::set_inf(acc);
+    for (uint32_t p = 0; p < nparts; p++) {
+      XYZZ<F2> v = *reinterpret_cast<const XYZZ<F2>*>(partials + p * set + 5 * x1);
+      EC<F2>::add(acc, v);
+    }
+    *reinterpret_cast<XYZZ<F2>*>(sums + 5 * x1) = acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------ MSM driver
 // T_j[i] = 2^(c j) P_i for j < nwin (affine, table j at offset j * npts): one thread per point
 template <class F>
@@ -469,6 +494,12 @@ struct CurveImpl : CurveBackend {
                                               (const P1*)a.z_msm, (const P1*)a.pok_msm, (const P1*)a.tmp,
                                               (Affine<G1F>*)a.out_ar, (Affine<G2F>*)a.out_bs,
                                               (Affine<G1F>*)a.out_krs, (Affine<G1F>*)a.out_pok);
+    B200_CUDA(cudaGetLastError());
+  }
+
+  void sum_sets(const void* d_partials, uint32_t nparts, void* d_sums, cudaStream_t s) override {
+    k_sum_sets<G1F, G2F><<<6, 32, 0, s>>>((const uint8_t*)d_partials, nparts, (uint8_t*)d_sums);
+    prof_count_launches(1);
     B200_CUDA(cudaGetLastError());
   }
 

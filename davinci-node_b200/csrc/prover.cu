@@ -120,7 +120,8 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
   mapK[npriv + 2] = SKIP;
   mapK[npriv + 3] = (uint32_t)ik;       // (-rs) * delta
   pk->nZ = d.g1_Z.len;
-  if (pk->nZ > pk->n) throw std::runtime_error("len(G1.Z) > domain size");
+  pk->z_offset = d.z_offset;
+  if (pk->z_offset + pk->nZ > pk->n) throw std::runtime_error("z_offset + len(G1.Z) > domain size");
 
   // ---- commitment keys: concatenated sigma bases, per-commitment bases
   pk->commit_n.resize(d.nb_commitments);
@@ -209,7 +210,8 @@ PkInstance& ProvingKeyDev::pick(int device) {
 }
 
 // ------------------------------------------------------------------------------------ prove
-void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, int device, bool inputs_on_device) {
+void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, int device, bool inputs_on_device,
+                          void* d_partials) {
   PkInstance& I = pick(device);
   PkSlot& S = I.acquire();
   std::lock_guard<std::mutex> lk(S.mu, std::adopt_lock);
@@ -262,7 +264,7 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
     B200_CUDA(cudaMemcpyAsync(c, in.c.ptr, nc * frb, kind, s0));
   }
   cb->compute_h(I.dom, a, b, c, s0);
-  cb->msm(1, nullptr, a, nZ, o_z, S.ws[0], s0, 0, nullptr, nullptr, &I.tZ);
+  cb->msm(1, nullptr, a + z_offset * frb, nZ, o_z, S.ws[0], s0, 0, nullptr, nullptr, &I.tZ);
   cb->msm(1, nullptr, W + nb_public * frb, m - nb_public + 4, o_k, S.ws[0], s0, 0, nullptr,
           (const uint32_t*)I.mapK.p, &I.tK);
   bool have_pok = total_commit > 0 || !commit_n.empty();
@@ -290,6 +292,13 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   }
   B200_CUDA(cudaStreamWaitEvent(s0, S.ev[1], 0));
   B200_CUDA(cudaStreamWaitEvent(s0, S.ev[2], 0));
+  if (d_partials) {
+    // range-split mode: hand the raw partial sums back (layout of msm_out: 5 G1 XYZZ then 1 G2 XYZZ)
+    if (!have_pok) B200_CUDA(cudaMemsetAsync(o_pok, 0, x1, s0));
+    B200_CUDA(cudaMemcpyAsync(d_partials, mo, 5 * x1 + x2, cudaMemcpyDeviceToDevice, s0));
+    B200_CUDA(cudaStreamSynchronize(s0));
+    return;
+  }
 
   uint8_t* oa = (uint8_t*)S.out_aff.p;   // ar, krs, pok (G1), bs (G2)
   AssembleArgs aa{};
@@ -312,7 +321,6 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   if (have_pok && out.pok) B200_CUDA(cudaMemcpyAsync(out.pok, oa + 2 * g1b, g1b, back, s0));
   B200_CUDA(cudaMemcpyAsync(out.bs, oa + 3 * g1b, g2b, back, s0));
   B200_CUDA(cudaStreamSynchronize(s0));
-  (void)x2;
 }
 
 // commitment i = sum_j values[j] * Basis_i[j]   (called from the solver hint, synchronous)

@@ -44,7 +44,7 @@ struct PkInstance {
 
 struct ProvingKeyDev {
   CurveBackend* cb = nullptr;
-  uint64_t n = 0, m = 0, nb_public = 0, nA = 0, nB = 0, nK = 0, nZ = 0, total_commit = 0;
+  uint64_t n = 0, m = 0, nb_public = 0, nA = 0, nB = 0, nK = 0, nZ = 0, total_commit = 0, z_offset = 0;
   int logn = 0;
   std::vector<uint64_t> commit_n;
   std::vector<std::unique_ptr<PkInstance>> inst;
@@ -52,7 +52,9 @@ struct ProvingKeyDev {
 
   static std::unique_ptr<ProvingKeyDev> create(const b200_pk_desc& d, const std::vector<int>& devices);
   PkInstance& pick(int device);
-  void prove(const b200_prove_in& in, const b200_proof_out& out, int device, bool inputs_on_device);
+  // d_partials != nullptr: range-split mode - skip the assembly and emit the six raw partial sums
+  void prove(const b200_prove_in& in, const b200_proof_out& out, int device, bool inputs_on_device,
+             void* d_partials = nullptr);
   void commit(uint32_t i, const b200_slice& values, void* out_affine, int device);
 };
 

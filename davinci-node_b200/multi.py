@@ -57,3 +57,108 @@ def msm_range_split(curve_id, grp, d_points_local, d_scalars_local, n_local, gro
     capi.check(capi.lib.b200_sum_partials_dev(L.id, grp, allp.data_ptr(), count, out.data_ptr(), st))
     torch.cuda.synchronize()
     return out.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# Range-split PROVE: one large proof over several GPUs (aggregator / statetransition)
+def slice_proving_key(pk, ccs, world, rank):
+    """The part of a gnark proving key GPU `rank` holds: the wire-indexed arrays (A, B, K and the
+    infinity flags) restricted to its wire range, its range of Z, and - on rank 0 only - alpha / beta /
+    delta and the commitment keys.  Returns (sub_pk, sub_ccs, info) ready for register_proving_key."""
+    from .gnark_types import ConstraintSystem, ProvingKey
+    from .layout import Layout
+    L = Layout(pk.curve_id)
+    g1b, g2b = L.affine_bytes(1), L.affine_bytes(2)
+    m = len(pk.infinity_a)
+    wlo, whi = shard_range(m, world, rank)
+    infA = np.asarray(pk.infinity_a, dtype=np.uint8)
+    infB = np.asarray(pk.infinity_b, dtype=np.uint8)
+    cumA = np.concatenate([[0], np.cumsum(infA == 0)])
+    cumB = np.concatenate([[0], np.cumsum(infB == 0)])
+    skip = np.zeros(m, dtype=bool)
+    for w in ccs.krs_skip_wires():
+        skip[w] = True
+    in_k = np.ones(m, dtype=bool)
+    in_k[:ccs.nb_public] = False
+    in_k &= ~skip
+    cumK = np.concatenate([[0], np.cumsum(in_k)])
+    nz = len(pk.g1_Z) // g1b
+    zlo, zhi = shard_range(nz, world, rank)
+    zero1, zero2 = np.zeros(g1b, dtype=np.uint8), np.zeros(g2b, dtype=np.uint8)
+    first = rank == 0
+    pts = lambda buf, lo, hi, sz: np.ascontiguousarray(buf[lo * sz:hi * sz])
+    sub = ProvingKey(
+        curve_id=pk.curve_id, domain_cardinality=pk.domain_cardinality,
+        domain_generator=pk.domain_generator, domain_coset_gen=pk.domain_coset_gen,
+        g1_alpha=pk.g1_alpha if first else zero1, g1_beta=pk.g1_beta if first else zero1,
+        g1_delta=pk.g1_delta if first else zero1,
+        g1_A=pts(pk.g1_A, cumA[wlo], cumA[whi], g1b), g1_B=pts(pk.g1_B, cumB[wlo], cumB[whi], g1b),
+        g1_Z=pts(pk.g1_Z, zlo, zhi, g1b), g1_K=pts(pk.g1_K, cumK[wlo], cumK[whi], g1b),
+        g2_beta=pk.g2_beta if first else zero2, g2_delta=pk.g2_delta if first else zero2,
+        g2_B=pts(pk.g2_B, cumB[wlo], cumB[whi], g2b),
+        infinity_a=infA[wlo:whi].copy(), infinity_b=infB[wlo:whi].copy(),
+        commitment_keys=list(pk.commitment_keys) if first else [])
+    nb_public_local = int(min(max(ccs.nb_public - wlo, 0), whi - wlo))
+    local_skip = sorted(int(w - wlo) for w in ccs.krs_skip_wires() if wlo <= w < whi)
+    # the sub constraint system only carries what registration reads (sizes and the K skip list)
+    sub_ccs = ConstraintSystem(curve_id=pk.curve_id, nb_wires=whi - wlo, nb_public=nb_public_local, nb_secret=0,
+                               L=[], R=[], O=[], commitments=[{"private_committed": local_skip, "commitment_index": None}]
+                               if local_skip else [])
+    sub_ccs.krs_skip_wires = lambda: set(local_skip)
+    return sub, sub_ccs, {"wire_range": (wlo, whi), "z_offset": zlo, "first": first}
+
+
+def register_key_slice(sub_pk, sub_ccs, info):
+    """b200_pk_register for one slice (z_offset set); returns the handle."""
+    from . import prover
+    return prover.register_proving_key(sub_pk, sub_ccs, z_offset=info["z_offset"])
+
+
+def prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_committed_dev=None):
+    """Partial sums of one key slice: W_dev is the FULL wire vector on this device (the slice is taken
+    here), a/b/c are full.  Returns a device tensor of 5*xyzz(1)+xyzz(2) bytes."""
+    import ctypes as C
+    import torch
+    from . import capi
+    frb = L.fr_bytes
+    wlo, whi = info["wire_range"]
+    rs = torch.from_numpy(np.concatenate([L.enc_fr([r]), L.enc_fr([s])])).cuda()
+    pin = capi.ProveIn()
+    pin.wires = capi.Slice(W_dev.data_ptr() + wlo * frb, whi - wlo)
+    pin.a, pin.b, pin.c = (capi.Slice(t.data_ptr(), nc) for t in (a_dev, b_dev, c_dev))
+    pin.r, pin.s = rs.data_ptr(), rs.data_ptr() + frb
+    k = len(priv_committed_dev) if (priv_committed_dev and info["first"]) else 0
+    pin.nb_commitments = k
+    pcs = (capi.Slice * max(k, 1))()
+    for i in range(k):
+        t, cnt = priv_committed_dev[i]
+        pcs[i] = capi.Slice(t.data_ptr(), cnt)
+    pin.priv_committed = pcs
+    pin.fold_challenge = None
+    out = torch.zeros(5 * L.xyzz_bytes(1) + L.xyzz_bytes(2), dtype=torch.uint8, device="cuda")
+    capi.check(capi.lib.b200_prove_partial_dev(handle, C.byref(pin), out.data_ptr(), torch.cuda.current_device()))
+    return out
+
+
+def assemble(L, partials_dev, nparts, r, s, have_pok):
+    """Final assembly from the gathered partials; returns dict of affine byte arrays."""
+    import torch
+    from . import capi
+    frb, g1b, g2b = L.fr_bytes, L.affine_bytes(1), L.affine_bytes(2)
+    rs = torch.from_numpy(np.concatenate([L.enc_fr([r]), L.enc_fr([s])])).cuda()
+    out = torch.zeros(3 * g1b + g2b, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    capi.check(capi.lib.b200_assemble_dev(L.id, partials_dev.data_ptr(), nparts, rs.data_ptr(), rs.data_ptr() + frb,
+                                          1 if have_pok else 0, out.data_ptr(), st))
+    buf = out.cpu().numpy()
+    return {"Ar": buf[:g1b], "Krs": buf[g1b:2 * g1b], "CommitmentPok": buf[2 * g1b:3 * g1b], "Bs": buf[3 * g1b:]}
+
+
+def prove_range_split(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, have_pok, priv_committed_dev=None,
+                      group=None):
+    """One proof over all ranks of `group`: partial sums on every GPU, all-gather (NCCL / NVLink), local
+    assembly.  Every rank returns the same proof."""
+    import torch.distributed as dist
+    part = prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_committed_dev)
+    allp = gather_partials(part, group)
+    return assemble(L, allp, dist.get_world_size(group), r, s, have_pok)

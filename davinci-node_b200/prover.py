@@ -61,7 +61,7 @@ def SetRandomness(fn):
     _randomness = fn or _default_randomness
 
 
-def register_proving_key(pk: ProvingKey, ccs: ConstraintSystem):
+def register_proving_key(pk: ProvingKey, ccs: ConstraintSystem, z_offset=0):
     """Upload pk to the selected GPUs once; later proofs reuse the resident copy (the reference's
     icicle path does the same lazily inside gpugroth16.Prove, prover/prover_gpu.go:33-56)."""
     with _lock:
@@ -97,6 +97,7 @@ def register_proving_key(pk: ProvingKey, ccs: ConstraintSystem):
             sigma[i] = _slice(key["BasisExpSigma"], g1b)
         d.commit_basis = basis
         d.commit_basis_exp_sigma = sigma
+        d.z_offset = z_offset
         h = C.c_uint64(0)
         capi.check(capi.lib.b200_pk_register(C.byref(d), C.byref(h)))
         _registered[id(pk)] = (pk, h.value)

@@ -121,6 +121,9 @@ typedef struct {
   uint32_t nb_commitments;        /* len(pk.CommitmentKeys) */
   const b200_slice* commit_basis;            /* pk.CommitmentKeys[i].Basis */
   const b200_slice* commit_basis_exp_sigma;  /* pk.CommitmentKeys[i].BasisExpSigma */
+  uint64_t z_offset;              /* 0 for a whole key.  Range-split keys (one slice of the key per GPU,
+                                     SURVEY.md 8e-2): g1_Z holds Z[z_offset .. z_offset+len) and pairs with
+                                     h[z_offset ..]; the wire-indexed arrays are sliced by the caller */
 } b200_pk_desc;
 
 typedef struct {
@@ -150,6 +153,17 @@ B200_API int b200_commit(uint64_t handle, uint32_t i, b200_slice values, void* o
 B200_API int b200_prove(uint64_t handle, const b200_prove_in* in, const b200_proof_out* out, int device);
 /* same, every pointer in `in` / `out` is a device pointer on the key's device (resident pipeline) */
 B200_API int b200_prove_dev(uint64_t handle, const b200_prove_in* in, const b200_proof_out* out, int device);
+
+/* Range-split proving (one large proof over several GPUs).  Every GPU holds a slice of the
+ * key (b200_pk_register with a sliced descriptor) and runs b200_prove_partial_dev on its slice of the wire
+ * vector and the FULL a, b, c: it writes its six un-normalised partial sums
+ *   [Ar, Bs1, K, Z, Pok (G1 XYZZ each), Bs (G2 XYZZ)]  =  5 * xyzz_bytes(1) + xyzz_bytes(2) bytes.
+ * The caller all-gathers them over NVLink (NCCL cannot reduce with the group law) and any GPU finishes with
+ * b200_assemble_dev, which adds the `nparts` partials per element and performs the same assembly as
+ * b200_prove (s*Ar + r*Bs1, affine normalisation).  d_out: Ar | Krs | Pok (G1 affine) | Bs (G2 affine). */
+B200_API int b200_prove_partial_dev(uint64_t handle, const b200_prove_in* in, void* d_partials_out, int device);
+B200_API int b200_assemble_dev(int curve, const void* d_partials, uint32_t nparts, const void* d_r, const void* d_s,
+                               int have_pok, void* d_out, void* cuda_stream);
 
 /* ---- EIP-4844 blob commitment (BLS12-381) -----------------------------------------------------
  * Replaces gethkzg.BlobToCommitment (types/blobs.go:90-96). */

@@ -134,3 +134,44 @@ def test_setup_mirror_matches_oracle_and_proves(env, cname):
     finally:
         prover.SetRandomness(None)
         prover.release_proving_key(pk)
+
+
+@pytest.mark.parametrize("cname,parts", [("bls12_377", 2), ("bw6_761", 3)])
+def test_range_split_prove_single_gpu(env, cname, parts):
+    """Range-split prove with all key slices on ONE device: per-slice partial sums,
+    concatenated as an all-gather would deliver them, assembled - bit-identical to the oracle's proof.
+    (tests/test_gpu_multi.py runs the same through NCCL on 2+ GPUs.)"""
+    import torch
+    from oracle_bridge import ccs_from_oracle, pk_from_oracle
+    from davinci_node_b200 import multi
+    capi, layout, prover, T = env
+    cx = OC.ctx(cname)
+    q = cx.r
+    L = layout.Layout(cname)
+    rnd = random.Random(2024 + parts)
+    cs, W = OG.synthetic_circuit(50, 5, q, seed=parts, n_commit=1, n_private_committed=4)
+    tox = OG.Toxic(*(rnd.randrange(1, q) for _ in range(5)), sigmas=[rnd.randrange(1, q)])
+    opk, ex = OG.setup(cs, cx, tox)
+    ccs, pk = ccs_from_oracle(cs, L.id), pk_from_oracle(opk, L.id)
+    r, s = rnd.randrange(q), rnd.randrange(q)
+    want = OG.prove(cs, opk, W, r, s, cx)
+    a, b, c = OG.constraint_values(cs, W, q)
+    dev = lambda v: torch.from_numpy(L.enc_fr(v)).cuda()
+    Wd, ad, bd, cd = dev(W), dev(a), dev(b), dev(c)
+    committed = cs.commitments[0]["private_committed"]
+    pc = [(dev([W[i] for i in committed]), len(committed))]
+    partials, subs = [], []
+    try:
+        for rank in range(parts):
+            sub, sub_ccs, info = multi.slice_proving_key(pk, ccs, parts, rank)
+            h = multi.register_key_slice(sub, sub_ccs, info)
+            subs.append(sub)
+            partials.append(multi.prove_partial(h, L, info, Wd, ad, bd, cd, len(a), r, s, pc))
+        got = multi.assemble(L, torch.cat(partials), parts, r, s, have_pok=True)
+        assert L.dec_affine(got["Ar"], 1)[0] == want["Ar"]
+        assert L.dec_affine(got["Bs"], 2)[0] == want["Bs"]
+        assert L.dec_affine(got["Krs"], 1)[0] == want["Krs"]
+        assert L.dec_affine(got["CommitmentPok"], 1)[0] == want["CommitmentPok"]
+    finally:
+        for sub in subs:
+            prover.release_proving_key(sub)
