@@ -37,6 +37,33 @@ def _worker(rank, world, port, q):
         ds = torch.from_numpy(L.enc_fr(sc[lo:hi])).cuda()
         got = L.dec_affine(multi.msm_range_split(L.id, grp, dp, ds, hi - lo), grp)[0]
         out[cname] = (got == cx.group(grp).msm(pts, sc))
+    # ---- range-split PROVE over NCCL: each rank holds a slice of an oracle-generated key
+    from davinci_node_b200 import prover
+    from oracle import groth16 as OG
+    from oracle_bridge import ccs_from_oracle, pk_from_oracle
+    cname = "bls12_377"
+    cx = OC.ctx(cname)
+    L = layout.Layout(cname)
+    qf = cx.r
+    rnd = random.Random(4321)
+    cs, W = OG.synthetic_circuit(40, 4, qf, seed=8, n_commit=1, n_private_committed=3)
+    tox = OG.Toxic(*(rnd.randrange(1, qf) for _ in range(5)), sigmas=[rnd.randrange(1, qf)])
+    opk, ex = OG.setup(cs, cx, tox)
+    ccs, pk = ccs_from_oracle(cs, L.id), pk_from_oracle(opk, L.id)
+    r, s = rnd.randrange(qf), rnd.randrange(qf)
+    want = OG.prove(cs, opk, W, r, s, cx)
+    a, b, c = OG.constraint_values(cs, W, qf)
+    dev = lambda v: torch.from_numpy(L.enc_fr(v)).cuda()
+    Wd, ad, bd, cd = dev(W), dev(a), dev(b), dev(c)
+    committed = cs.commitments[0]["private_committed"]
+    pc = [(dev([W[i] for i in committed]), len(committed))]
+    sub, sub_ccs, info = multi.slice_proving_key(pk, ccs, world, rank)
+    h = multi.register_key_slice(sub, sub_ccs, info)
+    got = multi.prove_range_split(h, L, info, Wd, ad, bd, cd, len(a), r, s, True, pc)
+    out["prove_split"] = (L.dec_affine(got["Ar"], 1)[0] == want["Ar"] and L.dec_affine(got["Bs"], 2)[0] == want["Bs"]
+                          and L.dec_affine(got["Krs"], 1)[0] == want["Krs"]
+                          and L.dec_affine(got["CommitmentPok"], 1)[0] == want["CommitmentPok"])
+    prover.release_proving_key(sub)
     q.put((rank, out))
     dist.destroy_process_group()
 
