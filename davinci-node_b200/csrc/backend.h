@@ -60,7 +60,7 @@ struct DevBuf {
 
 // Scratch for one MSM in flight (one per stream).
 struct MsmWorkspace {
-  DevBuf hist, off, cur, sorted, buckets, tasks, obuckets, partial, groups, windows, ctr, perm, bins;
+  DevBuf hist, off, cur, sorted, chunk_sums, buckets, tasks, obuckets, partial, mid, groups, windows, ctr, perm, bins;
 };
 
 // A base-point set with its precomputed window multiples resident in HBM ("table mode", msm_plan.h)
@@ -68,6 +68,20 @@ struct MsmBases {
   DevBuf tables;      // nwin tables of npts affine points: T_j[i] = 2^(c j) P_i
   uint64_t npts = 0;
   int c = 0, nwin = 0, group = 1;
+};
+
+}  // namespace b200
+#include "msm_plan.h"
+namespace b200 {
+
+// Output of the digit / counting-sort stage (device pointers into the sorting workspace): entries of
+// bucket array a live at sorted[a * pl.stride + off[a * nb + b] .. end[a * nb + b])
+struct MsmSorted {
+  MsmPlan pl;
+  uint32_t* off = nullptr;
+  uint32_t* end = nullptr;
+  uint32_t* sorted = nullptr;
+  uint32_t* totals = nullptr;
 };
 
 struct MsmStats {
@@ -121,6 +135,16 @@ struct CurveBackend {
   virtual void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out_xyzz,
                    MsmWorkspace& ws, cudaStream_t s, int c_override, MsmStats* stats,
                    const uint32_t* d_index_map = nullptr, const MsmBases* bases = nullptr) = 0;
+  // Shared-scalar MSMs (table mode): ONE digit/sort pass over `n` scalars feeds up to 4 base sets, set j
+  // taking point maps[j][i] for scalar i (0xffffffff = skip).  msm_reduce then accumulates and reduces
+  // `count` consecutive sets (their tables in `bases`, all of `group`) into `count` XYZZ results; a G1 and a
+  // G2 key over the same wires (Groth16's B) reduce the same sorted set twice.
+  virtual void msm_sort(const void* d_scalars, uint64_t n, const MsmBases* const* bases, const uint32_t* const* maps,
+                        int nsets, MsmWorkspace& ws, cudaStream_t s, MsmSorted& out) = 0;
+  virtual void msm_reduce(int group, const MsmSorted& so, int first_set, int count, const MsmBases* const* bases,
+                          void* d_out_xyzz, MsmWorkspace& ws, cudaStream_t s) = 0;
+  // window width the cost model picks for a table-mode base set of npts points
+  virtual int table_window(uint64_t npts) const = 0;
   // precompute T_j[i] = 2^(c j) P_i for a base set (window_bits = 0: cost model)
   virtual void build_tables(MsmBases& b, int group, const void* d_points, uint64_t npts, int window_bits,
                             cudaStream_t s) = 0;

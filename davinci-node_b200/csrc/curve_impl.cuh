@@ -242,27 +242,49 @@ __global__ void __launch_bounds__(64) k_build_tables(const Affine<F>* __restrict
   }
 }
 
-template <class F, class Fr, int GROUP>
-void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d_out, MsmWorkspace& ws,
-                cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map, const MsmBases* bases) {
-  using Pt = XYZZ<F>;
-  if (n >= (1ull << 31)) throw std::runtime_error("msm: n must be < 2^31");
-  MsmPlan pl = bases ? make_msm_plan_table(n, Fr::BITS, bases->c, bases->npts) : make_msm_plan(n, Fr::BITS, c_override);
-  if (stats) *stats = MsmStats{pl.c, pl.nwin, pl.nb, pl.task, pl.group};
-  if (n == 0) {
-    B200_CUDA(cudaMemsetAsync(d_out, 0, sizeof(Pt), s));
-    return;
-  }
+// ---- stage 1: digits -> per-bucket-array counting sort of (table index | sign) entries
+template <class Fr>
+void msm_sort_launch(const void* d_scalars, const MsmPlan& pl, const MsmSets& sets, MsmWorkspace& ws, cudaStream_t s,
+                     MsmSorted& out) {
   const uint64_t total_b = (uint64_t)pl.bwin * pl.nb;
-  const uint32_t ngroups = pl.nb / pl.group;
   uint32_t* hist = (uint32_t*)ws.hist.get(total_b * 4);
   uint32_t* off = (uint32_t*)ws.off.get(total_b * 4);
   uint32_t* cur = (uint32_t*)ws.cur.get(total_b * 4);
   uint32_t* sorted = (uint32_t*)ws.sorted.get((uint64_t)pl.bwin * pl.stride * 4);
+  const unsigned nchunks = (unsigned)((pl.nb + kScanChunk - 1) / kScanChunk);
+  if (nchunks > 1024) throw std::runtime_error("msm: too many buckets per array");
+  uint32_t* chunk_sums = (uint32_t*)ws.chunk_sums.get(((uint64_t)pl.bwin * nchunks + pl.bwin) * 4);
+  uint32_t* totals = chunk_sums + (uint64_t)pl.bwin * nchunks;
+  B200_CUDA(cudaMemsetAsync(hist, 0, total_b * 4, s));
+  const auto* sc = reinterpret_cast<const typename Fr::El*>(d_scalars);
+  const unsigned sblocks = (unsigned)((pl.n + 255) / 256);
+  k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, sets);
+  k_msm_scan_sums<<<dim3(nchunks, pl.bwin), kScanThreads, 0, s>>>(hist, pl, chunk_sums);
+  k_msm_scan<<<dim3(nchunks, pl.bwin), kScanThreads, 0, s>>>(hist, pl, chunk_sums, off, cur, totals);
+  k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, sets);
+  prof_count_launches(4);
+  B200_CUDA(cudaGetLastError());
+  out.pl = pl;
+  out.off = off;
+  out.end = cur;
+  out.sorted = sorted;
+  out.totals = totals;
+}
+
+// ---- stage 2: bucket accumulation + reduction of `pl.bwin` bucket arrays -> d_out (one XYZZ point in
+// windowed mode, one per base set in table mode)
+template <class F, int GROUP>
+void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmWorkspace& ws, cudaStream_t s) {
+  using Pt = XYZZ<F>;
+  const MsmPlan& pl = so.pl;
+  const uint64_t total_b = (uint64_t)pl.bwin * pl.nb;
+  const uint32_t ngroups = pl.nb / pl.group;
   Pt* buckets = (Pt*)ws.buckets.get(total_b * sizeof(Pt));
   OvfTask* tasks = (OvfTask*)ws.tasks.get((uint64_t)pl.max_ovf * sizeof(OvfTask));
   OvfBucket* obuckets = (OvfBucket*)ws.obuckets.get((uint64_t)pl.max_ovf * sizeof(OvfBucket));
   Pt* partial = (Pt*)ws.partial.get((uint64_t)pl.max_ovf * sizeof(Pt));
+  const uint32_t max_mid = pl.max_ovf / kOvfChunk + pl.max_ovf / kOvfSmall + 2;
+  Pt* mid = (Pt*)ws.mid.get((uint64_t)max_mid * sizeof(Pt));
   // window sums run in one or two slice-sum levels
   const uint32_t kSlices = 64;
   const bool two_level = ngroups >= 4 * kSlices;
@@ -271,34 +293,28 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
   Pt* windows = (Pt*)ws.windows.get((uint64_t)pl.bwin * sizeof(Pt));
   OvfCounters* ctr = (OvfCounters*)ws.ctr.get(sizeof(OvfCounters));
   uint32_t* perm = (uint32_t*)ws.perm.get(total_b * 4);
-  uint32_t* bins = (uint32_t*)ws.bins.get((2 * kSizeBins + pl.bwin) * 4);   // [bins | cursor | window totals]
-  uint32_t* totals = bins + 2 * kSizeBins;
+  uint32_t* bins = (uint32_t*)ws.bins.get(2 * kSizeBins * 4);   // [bins | cursor]
 
-  B200_CUDA(cudaMemsetAsync(hist, 0, total_b * 4, s));
   B200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(OvfCounters), s));
   B200_CUDA(cudaMemsetAsync(bins, 0, 2 * kSizeBins * 4, s));
-  const auto* sc = reinterpret_cast<const typename Fr::El*>(d_scalars);
-  const auto* pts = reinterpret_cast<const Affine<F>*>(bases ? bases->tables.p : d_points);
-  const unsigned sblocks = (unsigned)((n + 255) / 256);
-  const int tok_total = prof_begin(GROUP == 2 ? PROF_MSM_TOTAL_G2 : PROF_MSM_TOTAL_G1, s);
-  k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, d_index_map);
-  k_msm_scan<<<pl.bwin, 1024, 0, s>>>(hist, pl, off, cur, totals);
-  k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, d_index_map);
   // size-sorted bucket schedule
   const unsigned szblocks = (unsigned)((total_b + kSizeThreads * kSizePerThread - 1) / (kSizeThreads * kSizePerThread));
-  k_msm_size_hist<<<szblocks, kSizeThreads, 0, s>>>(off, cur, total_b, bins);
+  k_msm_size_hist<<<szblocks, kSizeThreads, 0, s>>>(so.off, so.end, total_b, bins);
   k_msm_size_scan<<<1, kSizeBins, 0, s>>>(bins, bins + kSizeBins);
-  k_msm_size_scatter<<<szblocks, kSizeThreads, 0, s>>>(off, cur, total_b, bins + kSizeBins, perm);
+  k_msm_size_scatter<<<szblocks, kSizeThreads, 0, s>>>(so.off, so.end, total_b, bins + kSizeBins, perm);
   const int tok_acc = prof_begin(GROUP == 2 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1, s);
-  k_msm_accumulate<F><<<(unsigned)((total_b + B200_ACC_THREADS - 1) / B200_ACC_THREADS), B200_ACC_THREADS, 0, s>>>(pts, sorted, off, cur, perm, totals, pl,
-                                                                         buckets, tasks, obuckets, ctr);
+  k_msm_accumulate<F><<<(unsigned)((total_b + B200_ACC_THREADS - 1) / B200_ACC_THREADS), B200_ACC_THREADS, 0, s>>>(
+      pts, so.sorted, so.off, so.end, perm, so.totals, pl, buckets, obuckets, ctr);
   prof_end(tok_acc, s);
-  // oversized buckets (skewed scalar distributions, e.g. the many 1-valued witness wires)
+  // oversized buckets: task list, partial sums, then a small-bucket merge and a two-level tree for big ones
+  k_msm_ovf_expand<<<148, 256, 0, s>>>(obuckets, ctr, pl, tasks);
   unsigned ovf_blocks = (unsigned)std::min<uint64_t>((pl.max_ovf + 127) / 128, 148 * 8);
-  k_msm_ovf_accumulate<F><<<ovf_blocks, 128, 0, s>>>(pts, sorted, pl, tasks, ctr, partial);
+  k_msm_ovf_accumulate<F><<<ovf_blocks, 128, 0, s>>>(pts, so.sorted, pl, tasks, ctr, partial);
+  k_msm_ovf_merge_small<F><<<64, 64, 0, s>>>(obuckets, ctr, partial, buckets);
+  const size_t merge_smem = kOvfMergeThreads * sizeof(Pt);
+  k_msm_ovf_merge_l1<F><<<dim3(32, 64), kOvfMergeThreads, merge_smem, s>>>(obuckets, ctr, partial, mid);
+  k_msm_ovf_merge_l2<F><<<256, kOvfMergeThreads, merge_smem, s>>>(obuckets, ctr, mid, buckets);
   size_t red_smem = kReduceThreads * sizeof(Pt);
-  k_msm_ovf_merge<F><<<(unsigned)std::min<uint64_t>(pl.max_ovf, 1024), kReduceThreads, red_smem, s>>>(obuckets, ctr,
-                                                                                                      partial, buckets);
   k_msm_bucket_reduce<F><<<(pl.bwin * ngroups + 63) / 64, 64, 0, s>>>(buckets, pl, groups);
   if (two_level) {
     k_msm_slice_sum<F><<<pl.bwin * kSlices, kReduceThreads, red_smem, s>>>(groups, ngroups / kSlices, mids);
@@ -307,9 +323,17 @@ void msm_launch(const void* d_points, const void* d_scalars, uint64_t n, void* d
     k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, s>>>(groups, ngroups, windows);
   }
   k_msm_horner<F><<<1, 32, 0, s>>>(windows, pl, (Pt*)d_out);
-  prof_end(tok_total, s);
   prof_count_launches(two_level ? 13 : 12);
   B200_CUDA(cudaGetLastError());
+}
+
+template <class F>
+void msm_set_smem_attrs() {
+  const int bytes = (int)(kOvfMergeThreads * sizeof(XYZZ<F>));
+  if (bytes > 48 * 1024) {
+    B200_CUDA(cudaFuncSetAttribute(k_msm_ovf_merge_l1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B200_CUDA(cudaFuncSetAttribute(k_msm_ovf_merge_l2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  }
 }
 
 // ------------------------------------------------------------------------------------ backend
@@ -332,9 +356,70 @@ struct CurveImpl : CurveBackend {
            cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map,
            const MsmBases* bases) override {
     if (bases && bases->group != group) throw std::runtime_error("msm: base tables belong to the other group");
-    if (group == 1) msm_launch<G1F, Fr, 1>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map, bases);
-    else msm_launch<G2F, Fr, 2>(d_points, d_scalars, n, d_out, ws, s, c_override, stats, d_index_map, bases);
+    if (n >= (1ull << 31)) throw std::runtime_error("msm: n must be < 2^31");
+    MsmPlan pl = bases ? make_msm_plan_table(n, Fr::BITS, bases->c, bases->npts) : make_msm_plan(n, Fr::BITS, c_override);
+    if (stats) *stats = MsmStats{pl.c, pl.nwin, pl.nb, pl.task, pl.group};
+    if (n == 0) {
+      B200_CUDA(cudaMemsetAsync(d_out, 0, xyzz_bytes(group), s));
+      return;
+    }
+    MsmSets sets{};
+    sets.map[0] = d_index_map;
+    sets.npts[0] = bases ? bases->npts : 0;
+    MsmPts pts{};
+    pts.p[0] = bases ? bases->tables.p : d_points;
+    MsmSorted so;
+    const int tok_total = prof_begin(group == 2 ? PROF_MSM_TOTAL_G2 : PROF_MSM_TOTAL_G1, s);
+    msm_sort_launch<Fr>(d_scalars, pl, sets, ws, s, so);
+    reduce_dispatch(group, so, pts, d_out, ws, s);
+    prof_end(tok_total, s);
   }
+
+  void reduce_dispatch(int group, const MsmSorted& so, const MsmPts& pts, void* d_out, MsmWorkspace& ws,
+                       cudaStream_t s) {
+    if (group == 1) {
+      msm_set_smem_attrs<G1F>();
+      msm_reduce_launch<G1F, 1>(so, pts, d_out, ws, s);
+    } else {
+      msm_set_smem_attrs<G2F>();
+      msm_reduce_launch<G2F, 2>(so, pts, d_out, ws, s);
+    }
+  }
+
+  void msm_sort(const void* d_scalars, uint64_t n, const MsmBases* const* bases, const uint32_t* const* maps,
+                int nsets, MsmWorkspace& ws, cudaStream_t s, MsmSorted& out) override {
+    if (nsets < 1 || nsets > kMaxSets) throw std::runtime_error("msm_sort: 1..4 base sets");
+    if (n == 0 || n >= (1ull << 31)) throw std::runtime_error("msm_sort: n must be in [1, 2^31)");
+    MsmSets sets{};
+    for (int j = 0; j < nsets; j++) {
+      if (bases[j]->c != bases[0]->c || bases[j]->nwin != bases[0]->nwin)
+        throw std::runtime_error("msm_sort: base sets must share the window width");
+      sets.map[j] = maps[j];
+      sets.npts[j] = bases[j]->npts;
+    }
+    MsmPlan pl = make_msm_plan_table(n, Fr::BITS, bases[0]->c, bases[0]->npts, nsets);
+    msm_sort_launch<Fr>(d_scalars, pl, sets, ws, s, out);
+  }
+
+  void msm_reduce(int group, const MsmSorted& so, int first_set, int count, const MsmBases* const* bases,
+                  void* d_out, MsmWorkspace& ws, cudaStream_t s) override {
+    if (!so.pl.table || first_set < 0 || count < 1 || first_set + count > so.pl.bwin)
+      throw std::runtime_error("msm_reduce: bad set range");
+    MsmSorted sub = so;
+    sub.pl = make_msm_plan_table(so.pl.n, Fr::BITS, so.pl.c, so.pl.npts, count);
+    sub.off += (uint64_t)first_set * so.pl.nb;
+    sub.end += (uint64_t)first_set * so.pl.nb;
+    sub.sorted += (uint64_t)first_set * so.pl.stride;
+    sub.totals += first_set;
+    MsmPts pts{};
+    for (int j = 0; j < count; j++) {
+      if (bases[j]->group != group) throw std::runtime_error("msm_reduce: base tables belong to the other group");
+      pts.p[j] = bases[j]->tables.p;
+    }
+    reduce_dispatch(group, sub, pts, d_out, ws, s);
+  }
+
+  int table_window(uint64_t npts) const override { return msm_table_window(npts, Fr::BITS); }
 
   void build_tables(MsmBases& b, int group, const void* d_points, uint64_t npts, int window_bits,
                     cudaStream_t s) override {

@@ -29,135 +29,267 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int bit, int 
   return (uint32_t)(two >> off) & ((1u << c) - 1u);
 }
 
-// Walk all windows of one scalar, calling f(w, bucket_index (0-based), negative)
-template <class Fr, class Fn>
-__device__ __forceinline__ void for_each_digit(const typename Fr::El& mont, const MsmPlan& pl, Fn f) {
-  typename Fr::El s;
-  Fr::from_mont(s, mont);
-  if (Fr::is_zero(s)) return;
+// Signed-digit recoding of one canonical scalar, window by window (carry kept between calls).
+// next() returns the 0-based bucket index of window w in `b` (digit magnitude - 1) and its sign;
+// false when the digit is zero.
+template <int NS>
+struct DigitWalker {
   uint32_t carry = 0;
-  const uint32_t half = 1u << (pl.c - 1);
-  for (int w = 0; w < pl.nwin; w++) {
-    uint32_t d = window_bits<Fr::N>(s.v, w * pl.c, pl.c) + carry;
+  __device__ __forceinline__ bool next(const uint32_t* s, int w, int c, uint32_t& b, bool& neg) {
+    uint32_t d = window_bits<NS>(s, w * c, c) + carry;
     carry = 0;
-    bool neg = false;
-    if (d > half) {
-      d = (1u << pl.c) - d;
+    neg = false;
+    if (d > (1u << (c - 1))) {
+      d = (1u << c) - d;
       neg = true;
       carry = 1;
     }
-    if (d) f(w, d - 1, neg);
+    b = d - 1;
+    return d != 0;
+  }
+};
+
+// The base sets one sorting pass feeds: scalar i multiplies point map[j][i] of set j (0xffffffff = not in
+// the set; a null map is the identity).  Windowed mode uses set 0 only.
+struct MsmSets {
+  const uint32_t* map[kMaxSets];
+  uint64_t npts[kMaxSets];
+};
+
+constexpr uint32_t kSkip = 0xffffffffu;
+
+// Shared front end of k_msm_hist / k_msm_scatter: loads scalar i, resolves its point index in every set and
+// converts it out of Montgomery form.  Returns false when the scalar contributes nothing.
+template <class Fr>
+__device__ __forceinline__ bool msm_load_scalar(const typename Fr::El* __restrict__ scalars, const MsmPlan& pl,
+                                                const MsmSets& sets, uint64_t i, typename Fr::El& s,
+                                                uint32_t (&pidx)[kMaxSets]) {
+  const int nsets = pl.table ? pl.bwin : 1;
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < kMaxSets; j++) {
+    pidx[j] = kSkip;
+    if (j < nsets && i < pl.n) {
+      pidx[j] = sets.map[j] ? sets.map[j][i] : (uint32_t)i;
+      any |= pidx[j] != kSkip;
+    }
+  }
+  if (!any) return false;
+  typename Fr::El mont;
+  load16(mont, scalars + i);
+  Fr::from_mont(s, mont);
+  return !Fr::is_zero(s);
+}
+
+// Window 0 is where solved witnesses collide (a fifth of the wires hold the value 1, many more hold small
+// integers): lanes of a warp that hit the same window-0 bucket are counted with ONE atomic (match_any +
+// popc) instead of serialising on one L2 address.  All 32 lanes must call these.
+template <class Fr>
+__global__ void __launch_bounds__(256)
+k_msm_hist(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ hist, MsmSets sets) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nsets = pl.table ? pl.bwin : 1;
+  const unsigned lane = threadIdx.x & 31u;
+  typename Fr::El s;
+  uint32_t pidx[kMaxSets];
+  bool live = msm_load_scalar<Fr>(scalars, pl, sets, i, s, pidx);
+  DigitWalker<Fr::N> dw;
+  uint32_t b = 0;
+  bool neg = false;
+  bool has0 = live && dw.next(s.v, 0, pl.c, b, neg);
+  const unsigned same = __match_any_sync(0xffffffffu, has0 ? b : (0x80000000u | lane));
+#pragma unroll
+  for (int j = 0; j < kMaxSets; j++) {
+    if (j >= nsets) break;
+    const bool in = has0 && pidx[j] != kSkip;
+    const unsigned grp = same & __ballot_sync(0xffffffffu, in);
+    if (in && lane == (unsigned)(__ffs(grp) - 1)) atomicAdd(&hist[(uint64_t)j * pl.nb + b], (uint32_t)__popc(grp));
+  }
+  if (!live) return;
+  for (int w = 1; w < pl.nwin; w++) {
+    if (!dw.next(s.v, w, pl.c, b, neg)) continue;
+    if (pl.table) {
+#pragma unroll
+      for (int j = 0; j < kMaxSets; j++)
+        if (j < nsets && pidx[j] != kSkip) atomicAdd(&hist[(uint64_t)j * pl.nb + b], 1u);
+    } else {
+      atomicAdd(&hist[(uint64_t)w * pl.nb + b], 1u);
+    }
   }
 }
 
-template <class Fr>
-__global__ void k_msm_hist(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ hist,
-                           const uint32_t* __restrict__ index_map) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= pl.n) return;
-  if (index_map && index_map[i] == 0xffffffffu) return;
-  typename Fr::El s;
-  load16(s, scalars + i);
-  const bool table = pl.bwin == 1;
-  for_each_digit<Fr>(s, pl, [&](int w, uint32_t b, bool) { atomicAdd(&hist[(table ? 0 : (uint64_t)w * pl.nb) + b], 1u); });
+// Exclusive scan of every bucket array's histogram -> off (segment starts) and cur (running cursors), plus
+// totals[a] = entries of bucket array a.  Two kernels over chunks of kScanChunk buckets: chunk sums, then
+// the in-chunk scan seeded with the sum of the earlier chunks (<= 2^10 chunks per array).
+constexpr int kScanItems = 16;
+constexpr int kScanThreads = 1024;
+constexpr uint32_t kScanChunk = kScanItems * kScanThreads;
+
+static __global__ void __launch_bounds__(kScanThreads)
+k_msm_scan_sums(const uint32_t* __restrict__ hist, MsmPlan pl, uint32_t* __restrict__ chunk_sums) {
+  __shared__ uint32_t warp_sums[32];
+  const uint32_t* h = hist + (uint64_t)blockIdx.y * pl.nb;
+  const uint32_t first = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) sum += first + k < pl.nb ? h[first + k] : 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t v = warp_sums[threadIdx.x];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (threadIdx.x == 0) chunk_sums[blockIdx.y * gridDim.x + blockIdx.x] = v;
+  }
 }
 
-// one block per bucket window: exclusive scan of hist -> off (start offsets) and cur (running cursors);
-// also totals[w] = number of (point, digit) entries of the window.  Each thread owns kScanItems
-// consecutive buckets per sweep, so 2^19 buckets take 32 sweeps instead of 512.
-constexpr int kScanItems = 16;
-static __global__ void __launch_bounds__(1024)
-k_msm_scan(const uint32_t* __restrict__ hist, MsmPlan pl, uint32_t* __restrict__ off, uint32_t* __restrict__ cur,
-           uint32_t* __restrict__ totals) {
+static __global__ void __launch_bounds__(kScanThreads)
+k_msm_scan(const uint32_t* __restrict__ hist, MsmPlan pl, const uint32_t* __restrict__ chunk_sums,
+           uint32_t* __restrict__ off, uint32_t* __restrict__ cur, uint32_t* __restrict__ totals) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
-  const uint32_t* h = hist + (uint64_t)blockIdx.x * pl.nb;
-  uint32_t* o = off + (uint64_t)blockIdx.x * pl.nb;
-  uint32_t* c = cur + (uint64_t)blockIdx.x * pl.nb;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const uint32_t per_sweep = blockDim.x * kScanItems;
-  for (uint32_t base = 0; base < pl.nb; base += per_sweep) {
-    uint32_t first = base + threadIdx.x * kScanItems;
-    uint32_t v[kScanItems];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-      v[k] = first + k < pl.nb ? h[first + k] : 0;
-      sum += v[k];
+  const uint32_t* h = hist + (uint64_t)blockIdx.y * pl.nb;
+  uint32_t* o = off + (uint64_t)blockIdx.y * pl.nb;
+  uint32_t* c = cur + (uint64_t)blockIdx.y * pl.nb;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // sum of the chunks before this one (and, in the last block, the array total)
+  if (wid == 0) {
+    const uint32_t* cs = chunk_sums + blockIdx.y * gridDim.x;
+    uint32_t before = 0, all = 0;
+    for (uint32_t k = lane; k < gridDim.x; k += 32) {
+      uint32_t v = cs[k];
+      all += v;
+      if (k < blockIdx.x) before += v;
     }
-    uint32_t x = sum;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, d);
+      all += __shfl_xor_sync(0xffffffffu, all, d);
+    }
+    if (lane == 0) {
+      carry_s = before;
+      if (blockIdx.x == 0) totals[blockIdx.y] = all;
+    }
+  }
+  __syncthreads();
+  const uint32_t first = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    v[k] = first + k < pl.nb ? h[first + k] : 0;
+    sum += v[k];
+  }
+  uint32_t x = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t ws = warp_sums[lane];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
-      if (lane >= d) x += y;
+      uint32_t y = __shfl_up_sync(0xffffffffu, ws, d);
+      if (lane >= d) ws += y;
     }
-    if (lane == 31) warp_sums[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-      uint32_t ws = lane < nw ? warp_sums[lane] : 0;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, ws, d);
-        if (lane >= d) ws += y;
-      }
-      warp_sums[lane] = ws;   // inclusive
-    }
-    __syncthreads();
-    uint32_t prefix = carry_s + (wid ? warp_sums[wid - 1] : 0) + (x - sum);
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-      if (first + k < pl.nb) {
-        o[first + k] = prefix;
-        c[first + k] = prefix;
-      }
-      prefix += v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = prefix;
-    __syncthreads();
+    warp_sums[lane] = ws;   // inclusive
   }
-  if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
+  __syncthreads();
+  uint32_t prefix = carry_s + (wid ? warp_sums[wid - 1] : 0) + (x - sum);
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    if (first + k < pl.nb) {
+      o[first + k] = prefix;
+      c[first + k] = prefix;
+    }
+    prefix += v[k];
+  }
 }
 
 template <class Fr>
-__global__ void k_msm_scatter(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ cur,
-                              uint32_t* __restrict__ sorted, const uint32_t* __restrict__ index_map) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= pl.n) return;
-  uint32_t pidx = (uint32_t)i;
-  if (index_map) {
-    pidx = index_map[i];
-    if (pidx == 0xffffffffu) return;
-  }
+__global__ void __launch_bounds__(256)
+k_msm_scatter(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ cur,
+              uint32_t* __restrict__ sorted, MsmSets sets) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nsets = pl.table ? pl.bwin : 1;
+  const unsigned lane = threadIdx.x & 31u;
   typename Fr::El s;
-  load16(s, scalars + i);
-  const bool table = pl.bwin == 1;
-  for_each_digit<Fr>(s, pl, [&](int w, uint32_t b, bool neg) {
-    uint32_t pos = atomicAdd(&cur[(table ? 0 : (uint64_t)w * pl.nb) + b], 1u);
-    // table mode: digit window w reads the precomputed multiple 2^(c w) P, stored at w * npts + i
-    uint32_t entry = table ? (uint32_t)((uint64_t)w * pl.npts + pidx) : pidx;
-    sorted[(table ? 0 : (uint64_t)w * pl.stride) + pos] = entry | (neg ? 0x80000000u : 0u);
-  });
+  uint32_t pidx[kMaxSets];
+  bool live = msm_load_scalar<Fr>(scalars, pl, sets, i, s, pidx);
+  DigitWalker<Fr::N> dw;
+  uint32_t b = 0;
+  bool neg = false;
+  bool has0 = live && dw.next(s.v, 0, pl.c, b, neg);
+  const unsigned same = __match_any_sync(0xffffffffu, has0 ? b : (0x80000000u | lane));
+#pragma unroll
+  for (int j = 0; j < kMaxSets; j++) {
+    if (j >= nsets) break;
+    const bool in = has0 && pidx[j] != kSkip;
+    const unsigned grp = same & __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const int leader = __ffs(grp) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(&cur[(uint64_t)j * pl.nb + b], (uint32_t)__popc(grp));
+      base = __shfl_sync(grp, base, leader);
+      const uint32_t pos = base + __popc(grp & ((1u << lane) - 1u));
+      // table mode: window 0 reads table 0 (the points themselves) at index pidx
+      sorted[(uint64_t)j * pl.stride + pos] = pidx[j] | (neg ? 0x80000000u : 0u);
+    }
+  }
+  if (!live) return;
+  for (int w = 1; w < pl.nwin; w++) {
+    if (!dw.next(s.v, w, pl.c, b, neg)) continue;
+    const uint32_t sign = neg ? 0x80000000u : 0u;
+    if (pl.table) {
+#pragma unroll
+      for (int j = 0; j < kMaxSets; j++) {
+        if (j < nsets && pidx[j] != kSkip) {
+          uint32_t pos = atomicAdd(&cur[(uint64_t)j * pl.nb + b], 1u);
+          // digit window w reads the precomputed multiple 2^(c w) P, stored at w * npts + index
+          sorted[(uint64_t)j * pl.stride + pos] = (uint32_t)((uint64_t)w * sets.npts[j] + pidx[j]) | sign;
+        }
+      }
+    } else {
+      uint32_t pos = atomicAdd(&cur[(uint64_t)w * pl.nb + b], 1u);
+      sorted[(uint64_t)w * pl.stride + pos] = pidx[0] | sign;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------ accumulate
 struct OvfTask {
-  uint32_t bucket;   // global bucket id  w * nb + b
-  uint32_t start;    // offset inside the window's sorted segment
+  uint32_t bucket;   // global bucket id  a * nb + b   (a = bucket array)
+  uint32_t start;    // offset inside the array's sorted segment
   uint32_t len;
   uint32_t pad;
 };
+// an oversized bucket: its points beyond the accumulate thread's cap are cut into `ntasks` tasks
+// (tasks / partial sums [first, first + ntasks)); buckets with many tasks are merged in two tree levels
+// (level-1 block sums at mid[first2 ...])
 struct OvfBucket {
   uint32_t bucket;
-  uint32_t first;    // first task index
+  uint32_t first;
   uint32_t ntasks;
-  uint32_t pad;
+  uint32_t start;    // first overflow entry inside the array's sorted segment
+  uint32_t len;      // overflow entries
+  uint32_t first2;
+  uint32_t pad0, pad1;
 };
 struct OvfCounters {
   uint32_t ntasks;
   uint32_t nbuckets;
+  uint32_t nmid;
+  uint32_t pad;
+};
+
+// device pointers of the point arrays a launch reads: one per base set in table mode, [0] otherwise
+struct MsmPts {
+  const void* p[kMaxSets];
 };
 
 template <class F>
@@ -285,8 +417,6 @@ k_msm_size_scatter(const uint32_t* __restrict__ off, const uint32_t* __restrict_
   }
 }
 
-constexpr uint32_t kOvfTask = kOvfTaskPoints;
-
 template <class F>
 #ifndef B200_ACC_NO_LOCKSTEP
 #define B200_ACC_LOCKSTEP 1   // measured: -5% (G1) / -8% (G2) accumulate time at 128 threads, 3 blocks per SM
@@ -298,11 +428,10 @@ template <class F>
 #define B200_ACC_THREADS 128
 #endif
 __global__ void __launch_bounds__(B200_ACC_THREADS, B200_ACC_MIN_BLOCKS)
-k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted,
-                 const uint32_t* __restrict__ off, const uint32_t* __restrict__ end,
-                 const uint32_t* __restrict__ perm, const uint32_t* __restrict__ totals, MsmPlan pl,
-                 XYZZ<F>* __restrict__ buckets, OvfTask* __restrict__ tasks, OvfBucket* __restrict__ obuckets,
-                 OvfCounters* __restrict__ ctr) {
+k_msm_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
+                 const uint32_t* __restrict__ end, const uint32_t* __restrict__ perm,
+                 const uint32_t* __restrict__ totals, MsmPlan pl, XYZZ<F>* __restrict__ buckets,
+                 OvfBucket* __restrict__ obuckets, OvfCounters* __restrict__ ctr) {
   uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = t < (uint64_t)pl.bwin * pl.nb;
 #ifndef B200_ACC_LOCKSTEP
@@ -312,28 +441,21 @@ k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restric
   uint32_t w = gb / pl.nb;
   uint32_t start = valid ? off[gb] : 0, cnt = valid ? end[gb] - start : 0;
   uint32_t mine = cnt;
-  // the cap follows the ACTUAL mean bucket load of this window (sparse witness vectors fill far fewer
-  // digits than n * nwin): a single thread's chain of additions is pure latency (~8 us each)
+  // the cap follows the ACTUAL mean bucket load of this array (sparse witness vectors fill far fewer
+  // digits than n * nwin): a single thread's chain of additions is pure latency (~10 us each)
   uint32_t task = 8u * (totals[w] / pl.nb + 1u);
   task = task < pl.task_min ? pl.task_min : (task > pl.task ? pl.task : task);
   if (cnt > task) {
-    mine = task;
     uint32_t extra = (cnt - task + pl.ovf_task - 1) / pl.ovf_task;
     uint32_t first = atomicAdd(&ctr->ntasks, extra);
     if (first + extra <= pl.max_ovf) {
+      mine = task;
       uint32_t ob = atomicAdd(&ctr->nbuckets, 1u);
-      obuckets[ob] = OvfBucket{gb, first, extra, 0};
-      uint32_t s = start + task, left = cnt - task;
-      for (uint32_t k = 0; k < extra; k++) {
-        uint32_t l = left < pl.ovf_task ? left : pl.ovf_task;
-        tasks[first + k] = OvfTask{gb, s, l, 0};
-        s += l;
-        left -= l;
-      }
-    } else {
-      mine = cnt;   // cannot happen (capacity is n*nwin/kOvfTask + 1); stay correct anyway
+      obuckets[ob] = OvfBucket{gb, first, extra, start + task, cnt - task, 0, 0, 0};
     }
+    // else: cannot happen (capacity covers every entry); stay correct anyway by taking the whole bucket
   }
+  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[pl.table ? w : 0]);
   XYZZ<F> acc;
 #ifdef B200_ACC_LOCKSTEP
   accumulate_run_lockstep<F>(acc, points, sorted + (uint64_t)w * pl.stride + start, mine);
@@ -344,15 +466,34 @@ k_msm_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restric
 #endif
 }
 
+// ---- oversized buckets (skewed scalar distributions, e.g. the many 1-valued witness wires)
+// one warp per oversized bucket writes its task list
+static __global__ void __launch_bounds__(256)
+k_msm_ovf_expand(const OvfBucket* __restrict__ obuckets, const OvfCounters* __restrict__ ctr, MsmPlan pl,
+                 OvfTask* __restrict__ tasks) {
+  const uint32_t nbk = ctr->nbuckets;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t ob = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ob < nbk; ob += warps) {
+    OvfBucket b = obuckets[ob];
+    for (uint32_t k = lane; k < b.ntasks; k += 32) {
+      uint32_t s = k * pl.ovf_task;
+      uint32_t l = b.len - s < pl.ovf_task ? b.len - s : pl.ovf_task;
+      tasks[b.first + k] = OvfTask{b.bucket, b.start + s, l, 0};
+    }
+  }
+}
+
 template <class F>
 __global__ void __launch_bounds__(128)
-k_msm_ovf_accumulate(const Affine<F>* __restrict__ points, const uint32_t* __restrict__ sorted, MsmPlan pl,
+k_msm_ovf_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, MsmPlan pl,
                      const OvfTask* __restrict__ tasks, const OvfCounters* __restrict__ ctr,
                      XYZZ<F>* __restrict__ partial) {
   uint32_t nt = ctr->ntasks < pl.max_ovf ? ctr->ntasks : pl.max_ovf;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     OvfTask tk = tasks[t];
     uint32_t w = tk.bucket / pl.nb;
+    const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[pl.table ? w : 0]);
     XYZZ<F> acc;
     accumulate_run<F>(acc, points, sorted + (uint64_t)w * pl.stride + tk.start, tk.len);
     store16(partial + t, acc);
@@ -377,26 +518,87 @@ __device__ __forceinline__ void block_sum(XYZZ<F>& v, XYZZ<F>* sm) {
 }
 
 constexpr int kReduceThreads = 64;
+constexpr uint32_t kOvfSmall = 8;                       // buckets with <= 8 partial sums: one thread adds them
+constexpr int kOvfMergeThreads = 128;
+constexpr uint32_t kOvfPre = 4;                         // partial sums a thread adds before the block tree
+constexpr uint32_t kOvfChunk = kOvfMergeThreads * kOvfPre;   // partial sums one level-1 block merges
 
-// one block per oversized bucket: bucket += sum of its task partials
+// thread per oversized bucket: few partial sums are added directly; many get a level-1 output range
 template <class F>
-__global__ void __launch_bounds__(kReduceThreads)
-k_msm_ovf_merge(const OvfBucket* __restrict__ obuckets, const OvfCounters* __restrict__ ctr,
-                const XYZZ<F>* __restrict__ partial, XYZZ<F>* __restrict__ buckets) {
-  extern __shared__ uint4 smem_raw[];
-  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+__global__ void __launch_bounds__(64)
+k_msm_ovf_merge_small(OvfBucket* __restrict__ obuckets, OvfCounters* __restrict__ ctr,
+                      const XYZZ<F>* __restrict__ partial, XYZZ<F>* __restrict__ buckets) {
   using E = EC<F>;
-  uint32_t nbk = ctr->nbuckets;
-  for (uint32_t ob = blockIdx.x; ob < nbk; ob += gridDim.x) {
+  const uint32_t nbk = ctr->nbuckets;
+  for (uint32_t ob = blockIdx.x * blockDim.x + threadIdx.x; ob < nbk; ob += gridDim.x * blockDim.x) {
     OvfBucket b = obuckets[ob];
+    if (b.ntasks > kOvfSmall) {
+      obuckets[ob].first2 = atomicAdd(&ctr->nmid, (b.ntasks + kOvfChunk - 1) / kOvfChunk);
+      continue;
+    }
     XYZZ<F> acc;
-    E::set_inf(acc);
-    for (uint32_t t = threadIdx.x; t < b.ntasks; t += kReduceThreads) {
+    load16_rw(acc, buckets + b.bucket);
+    for (uint32_t t = 0; t < b.ntasks; t++) {
       XYZZ<F> p;
       load16_rw(p, partial + b.first + t);
       E::add(acc, p);
     }
-    block_sum<F, kReduceThreads>(acc, sm);
+    store16(buckets + b.bucket, acc);
+  }
+}
+
+// level 1: block (x, y) sums chunk x (+ k gridDim.x) of the partial sums of big bucket y (+ k gridDim.y)
+template <class F>
+__global__ void __launch_bounds__(kOvfMergeThreads)
+k_msm_ovf_merge_l1(const OvfBucket* __restrict__ obuckets, const OvfCounters* __restrict__ ctr,
+                   const XYZZ<F>* __restrict__ partial, XYZZ<F>* __restrict__ mid) {
+  extern __shared__ uint4 smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  using E = EC<F>;
+  const uint32_t nbk = ctr->nbuckets;
+  for (uint32_t ob = blockIdx.y; ob < nbk; ob += gridDim.y) {
+    OvfBucket b = obuckets[ob];
+    if (b.ntasks <= kOvfSmall) continue;
+    const uint32_t nchunks = (b.ntasks + kOvfChunk - 1) / kOvfChunk;
+    for (uint32_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+      XYZZ<F> acc;
+      E::set_inf(acc);
+      const uint32_t base = ch * kOvfChunk + threadIdx.x * kOvfPre;
+      for (uint32_t k = 0; k < kOvfPre; k++) {
+        if (base + k < b.ntasks) {
+          XYZZ<F> p;
+          load16_rw(p, partial + b.first + base + k);
+          E::add(acc, p);
+        }
+      }
+      block_sum<F, kOvfMergeThreads>(acc, sm);
+      if (threadIdx.x == 0) store16(mid + b.first2 + ch, acc);
+      __syncthreads();
+    }
+  }
+}
+
+// level 2: one block per big bucket adds its level-1 sums into the bucket
+template <class F>
+__global__ void __launch_bounds__(kOvfMergeThreads)
+k_msm_ovf_merge_l2(const OvfBucket* __restrict__ obuckets, const OvfCounters* __restrict__ ctr,
+                   const XYZZ<F>* __restrict__ mid, XYZZ<F>* __restrict__ buckets) {
+  extern __shared__ uint4 smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  using E = EC<F>;
+  const uint32_t nbk = ctr->nbuckets;
+  for (uint32_t ob = blockIdx.x; ob < nbk; ob += gridDim.x) {
+    OvfBucket b = obuckets[ob];
+    if (b.ntasks <= kOvfSmall) continue;
+    const uint32_t nchunks = (b.ntasks + kOvfChunk - 1) / kOvfChunk;
+    XYZZ<F> acc;
+    E::set_inf(acc);
+    for (uint32_t ch = threadIdx.x; ch < nchunks; ch += kOvfMergeThreads) {
+      XYZZ<F> p;
+      load16_rw(p, mid + b.first2 + ch);
+      E::add(acc, p);
+    }
+    block_sum<F, kOvfMergeThreads>(acc, sm);
     if (threadIdx.x == 0) {
       XYZZ<F> cur;
       load16_rw(cur, buckets + b.bucket);
@@ -456,11 +658,21 @@ k_msm_slice_sum(const XYZZ<F>* __restrict__ in, uint32_t per_slice, XYZZ<F>* __r
   if (threadIdx.x == 0) store16(out + blockIdx.x, acc);
 }
 
-// result = sum_w 2^(c w) windows[w]   (single thread; latency hidden by the other MSM streams)
+// windowed mode: out[0] = sum_w 2^(c w) windows[w]  (single thread; latency hidden by the other MSM streams)
+// table mode: out[j] = windows[j], one result per base set (the tables already carry the 2^(c w) factors)
 template <class F>
 __global__ void k_msm_horner(const XYZZ<F>* __restrict__ windows, MsmPlan pl, XYZZ<F>* __restrict__ out) {
   using E = EC<F>;
-  if (threadIdx.x || blockIdx.x) return;
+  if (blockIdx.x) return;
+  if (pl.table) {
+    if ((int)threadIdx.x < pl.bwin) {
+      XYZZ<F> ws;
+      load16_rw(ws, windows + threadIdx.x);
+      store16(out + threadIdx.x, ws);
+    }
+    return;
+  }
+  if (threadIdx.x) return;
   XYZZ<F> acc;
   E::set_inf(acc);
   for (int w = pl.bwin - 1; w >= 0; w--) {

@@ -8,18 +8,22 @@
 
 namespace b200 {
 
-constexpr uint32_t kOvfTaskPoints = 128;   // points per overflow task (their latency is serial)
+constexpr uint32_t kOvfTaskPoints = 32;    // points per overflow task (a chain of mixed adds is pure latency, ~10 us each)
+constexpr int kMaxSets = 4;                // bucket sets one sorting pass can feed (table mode, shared scalar vector)
 
 // Two modes:
 //  * windowed (bwin == nwin): classic Pippenger, one bucket set per scalar window, Horner at the end.
 //  * table (bwin == 1): the base set carries precomputed multiples T_j[i] = 2^(c j) P_i resident in
 //    HBM, so every window's digit adds into ONE shared bucket set - no Horner, nwin times fewer
-//    buckets to reduce, which lets c grow (fewer point additions).
+//    buckets to reduce, which lets c grow (fewer point additions).  Several base sets that are multiplied
+//    by the SAME scalar vector (the A / B / K keys of a Groth16 proof all take the wire vector) share one
+//    digit/sort pass: bwin == nsets bucket sets, one per base set, each with its own index map.
 struct MsmPlan {
   uint64_t n;          // number of scalars
   int c;               // window width in bits
   int nwin;            // digit windows = ceil((scalar_bits + 1) / c)
-  int bwin;            // bucket windows: nwin (windowed) or 1 (table mode)
+  int bwin;            // bucket arrays: nwin (windowed) or the number of base sets (table mode)
+  int table;           // 1 = table mode
   uint32_t nb;         // buckets per bucket window = 2^(c-1)
   uint32_t task;       // max points a single thread accumulates for one bucket
   uint32_t task_min;   // lower bound of the load-adaptive cap
@@ -62,7 +66,7 @@ inline void msm_plan_finish(MsmPlan& pl) {
   pl.nb = 1u << (pl.c - 1);
   const uint64_t adds = pl.n * (uint64_t)pl.nwin;
   const uint64_t total_b = (uint64_t)pl.bwin * pl.nb;
-  uint64_t avg = adds / total_b + 1;
+  uint64_t avg = adds / (pl.table ? pl.nb : total_b) + 1;
   // large MSMs: size-sorted scheduling hides long buckets, keep overflow rare.  small MSMs: the longest
   // per-thread chain IS the latency, so cap it hard and split the rest into short parallel tasks.
   const bool small = adds < (1u << 21);
@@ -80,8 +84,8 @@ inline void msm_plan_finish(MsmPlan& pl) {
   if (g < 4) g = std::min<uint32_t>(4, pl.nb);
   pl.group = std::min<uint32_t>(g, pl.nb);
   // every overflowing bucket holds > task_min points and every overflow task but the last is full
-  pl.max_ovf = (uint32_t)(adds / pl.ovf_task + adds / pl.task_min + 2);
-  pl.stride = pl.bwin == 1 ? adds : pl.n;
+  pl.max_ovf = (uint32_t)((adds / pl.ovf_task + adds / pl.task_min + 2) * (pl.table ? pl.bwin : 1));
+  pl.stride = pl.table ? adds : pl.n;
 }
 
 inline MsmPlan make_msm_plan(uint64_t n, int scalar_bits, int c_override) {
@@ -102,17 +106,19 @@ inline MsmPlan make_msm_plan(uint64_t n, int scalar_bits, int c_override) {
   pl.c = c_override > 0 ? c_override : best_c;
   pl.nwin = msm_nwin(scalar_bits, pl.c);
   pl.bwin = pl.nwin;
+  pl.table = 0;
   pl.npts = 0;
   msm_plan_finish(pl);
   return pl;
 }
 
-inline MsmPlan make_msm_plan_table(uint64_t n, int scalar_bits, int c, uint64_t npts) {
+inline MsmPlan make_msm_plan_table(uint64_t n, int scalar_bits, int c, uint64_t npts, int nsets = 1) {
   MsmPlan pl{};
   pl.n = n;
   pl.c = c;
   pl.nwin = msm_nwin(scalar_bits, c);
-  pl.bwin = 1;
+  pl.bwin = nsets;
+  pl.table = 1;
   pl.npts = npts;
   msm_plan_finish(pl);
   return pl;

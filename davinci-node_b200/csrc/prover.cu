@@ -85,7 +85,8 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
 
   // ---- index maps over the extended wire vector  W_ext = [w_0 .. w_{m-1}, r, s, 1, -rs]
   const uint32_t SKIP = 0xffffffffu;
-  std::vector<uint32_t> mapA(pk->m + 4), mapB(pk->m + 4), mapK(pk->m - pk->nb_public + 4);
+  // (all three are indexed by the position in W_ext so that one sorting pass can feed A, B and K)
+  std::vector<uint32_t> mapA(pk->m + 4), mapB(pk->m + 4), mapK(pk->m + 4, SKIP);
   uint64_t ia = 0, ib = 0;
   for (uint64_t i = 0; i < pk->m; i++) {
     mapA[i] = infA[i] ? SKIP : (uint32_t)ia++;
@@ -110,15 +111,12 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
   for (uint64_t j = 0; j < npriv; j++) {
     uint64_t wire = pk->nb_public + j;
     while (si < nskip && skip[si] < wire) si++;
-    if (si < nskip && skip[si] == wire) mapK[j] = SKIP;
-    else mapK[j] = (uint32_t)ik++;
+    if (si < nskip && skip[si] == wire) mapK[wire] = SKIP;
+    else mapK[wire] = (uint32_t)ik++;
   }
   if (ik != d.g1_K.len) throw std::runtime_error("len(G1.K) != private wires - skipped wires");
   pk->nK = ik;
-  mapK[npriv + 0] = SKIP;
-  mapK[npriv + 1] = SKIP;
-  mapK[npriv + 2] = SKIP;
-  mapK[npriv + 3] = (uint32_t)ik;       // (-rs) * delta
+  mapK[pk->m + 3] = (uint32_t)ik;       // (-rs) * delta
   pk->nZ = d.g1_Z.len;
   pk->z_offset = d.z_offset;
   if (pk->z_offset + pk->nZ > pk->n) throw std::runtime_error("z_offset + len(G1.Z) > domain size");
@@ -140,19 +138,22 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
     cudaStream_t s = in->slots[0]->st[0];
     // upload (points || extra0 || extra1) to a staging buffer, build its window tables, drop the staging copy
     DevBuf stage;
-    auto put_tables = [&](MsmBases& t, int group, const b200_slice& sl, size_t pb, const void* e0, const void* e1) {
+    auto put_tables = [&](MsmBases& t, int group, const b200_slice& sl, size_t pb, const void* e0, const void* e1,
+                          int window_bits = 0) {
       uint64_t cnt = sl.len + (e0 ? 1 : 0) + (e1 ? 1 : 0);
       uint8_t* p = (uint8_t*)stage.get(std::max<uint64_t>(cnt, 1) * pb);
       if (sl.len) B200_CUDA(cudaMemcpyAsync(p, sl.ptr, sl.len * pb, cudaMemcpyHostToDevice, s));
       if (e0) B200_CUDA(cudaMemcpyAsync(p + sl.len * pb, e0, pb, cudaMemcpyHostToDevice, s));
       if (e1) B200_CUDA(cudaMemcpyAsync(p + (sl.len + 1) * pb, e1, pb, cudaMemcpyHostToDevice, s));
-      cb->build_tables(t, group, p, cnt, 0, s);
+      cb->build_tables(t, group, p, cnt, window_bits, s);
       B200_CUDA(cudaStreamSynchronize(s));   // staging buffer is reused by the next base set
     };
-    put_tables(in->tA, 1, d.g1_A, g1b, d.g1_delta, d.g1_alpha);
-    put_tables(in->tB1, 1, d.g1_B, g1b, d.g1_delta, d.g1_beta);
-    put_tables(in->tB2, 2, d.g2_B, g2b, d.g2_delta, d.g2_beta);
-    put_tables(in->tK, 1, d.g1_K, g1b, d.g1_delta, nullptr);
+    // the wire-indexed keys share one digit/sort pass per proof, hence one window width
+    const int cw = cb->table_window(std::max({d.g1_A.len + 2, d.g1_B.len + 2, d.g1_K.len + 1}));
+    put_tables(in->tA, 1, d.g1_A, g1b, d.g1_delta, d.g1_alpha, cw);
+    put_tables(in->tB1, 1, d.g1_B, g1b, d.g1_delta, d.g1_beta, cw);
+    put_tables(in->tB2, 2, d.g2_B, g2b, d.g2_delta, d.g2_beta, cw);
+    put_tables(in->tK, 1, d.g1_K, g1b, d.g1_delta, nullptr, cw);
     put_tables(in->tZ, 1, d.g1_Z, g1b, nullptr, nullptr);
     upload(in->mapA, mapA.data(), mapA.size() * 4, s);
     upload(in->mapB, mapB.data(), mapB.size() * 4, s);
@@ -242,16 +243,24 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   uint8_t *o_ar = mo, *o_bs1 = mo + x1, *o_k = mo + 2 * x1, *o_z = mo + 3 * x1, *o_pok = mo + 4 * x1,
           *o_bs2 = mo + 5 * x1;
 
-  // ---- s1: Ar, Bs1   s2: Bs (G2)
+  // ---- s1: ONE digit/sort pass over W_ext feeds the A, B and K keys; Ar, Bs1 and the wire part of Krs are
+  //         reduced together in G1.   s2: Bs (G2) reduces the B set of the same sorted data.
   B200_CUDA(cudaStreamWaitEvent(s1, S.ev[0], 0));
-  cb->msm(1, nullptr, W, m + 4, o_ar, S.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapA.p, &I.tA);
-  cb->msm(1, nullptr, W, m + 4, o_bs1, S.ws[1], s1, 0, nullptr, (const uint32_t*)I.mapB.p, &I.tB1);
-  B200_CUDA(cudaEventRecord(S.ev[1], s1));
-  B200_CUDA(cudaStreamWaitEvent(s2, S.ev[0], 0));
-  cb->msm(2, nullptr, W, m + 4, o_bs2, S.ws[2], s2, 0, nullptr, (const uint32_t*)I.mapB.p, &I.tB2);
-  B200_CUDA(cudaEventRecord(S.ev[2], s2));
+  {
+    const MsmBases* sets[3] = {&I.tA, &I.tB1, &I.tK};
+    const uint32_t* maps[3] = {(const uint32_t*)I.mapA.p, (const uint32_t*)I.mapB.p, (const uint32_t*)I.mapK.p};
+    MsmSorted so;
+    cb->msm_sort(W, m + 4, sets, maps, 3, S.ws[1], s1, so);
+    B200_CUDA(cudaEventRecord(S.ev[3], s1));
+    cb->msm_reduce(1, so, 0, 3, sets, o_ar, S.ws[1], s1);   // -> o_ar, o_bs1, o_k (contiguous)
+    B200_CUDA(cudaEventRecord(S.ev[1], s1));
+    B200_CUDA(cudaStreamWaitEvent(s2, S.ev[3], 0));
+    const MsmBases* g2set[1] = {&I.tB2};
+    cb->msm_reduce(2, so, 1, 1, g2set, o_bs2, S.ws[2], s2);
+    B200_CUDA(cudaEventRecord(S.ev[2], s2));
+  }
 
-  // ---- s0: quotient, Z and K MSMs, proof of knowledge
+  // ---- s0: quotient, Z MSM, proof of knowledge
   const uint64_t nc = in.a.len;
   if (nc < n) {
     B200_CUDA(cudaMemsetAsync(a + nc * frb, 0, (n - nc) * frb, s0));
@@ -265,8 +274,6 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   }
   cb->compute_h(I.dom, a, b, c, s0);
   cb->msm(1, nullptr, a + z_offset * frb, nZ, o_z, S.ws[0], s0, 0, nullptr, nullptr, &I.tZ);
-  cb->msm(1, nullptr, W + nb_public * frb, m - nb_public + 4, o_k, S.ws[0], s0, 0, nullptr,
-          (const uint32_t*)I.mapK.p, &I.tK);
   bool have_pok = total_commit > 0 || !commit_n.empty();
   if (have_pok) {
     uint8_t* cv = (uint8_t*)S.cvals.p;

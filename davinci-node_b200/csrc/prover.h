@@ -17,7 +17,7 @@ struct PkSlot {
   int device;
   std::mutex mu;
   cudaStream_t st[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   DevBuf W, a, b, c, rs, cvals, chal, msm_out, tmp, out_aff;
   MsmWorkspace ws[3];
   explicit PkSlot(int dev);
