@@ -72,6 +72,7 @@ _PROTOS = {
     "b200_launch_count": (_u64, []),
     "b200_profile_enable": (_i, [_i]),
     "b200_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(_u64)]),
+    "b200_profile_timeline": (_i, [C.POINTER(C.c_double), _u64, C.POINTER(_u64)]),
     "b200_prove_partial_dev": (_i, [_u64, C.POINTER(ProveIn), _vp, _i]),
     "b200_assemble_dev": (_i, [_i, _vp, _u32, _vp, _vp, _i, _vp, _vp]),
     "b200_kzg_srs_register": (_i, [_vp, _u32, C.POINTER(_u64)]),

@@ -24,7 +24,9 @@ struct CudaError : std::runtime_error {
 
 // ---- instrumentation (off by default): kernel launch counter and CUDA-event kernel timers
 enum ProfTag { PROF_MSM_ACC_G1 = 0, PROF_MSM_ACC_G2 = 1, PROF_NTT_PASS = 2, PROF_MSM_TOTAL_G1 = 3, PROF_MSM_TOTAL_G2 = 4,
-               PROF_TAGS = 5 };
+               PROF_TAGS = 5,   // tags below only appear in the timeline (b200_profile_timeline)
+               PROF_MSM_SORT = 5, PROF_MSM_SCHED = 6, PROF_MSM_OVF = 7, PROF_MSM_BUCKET_REDUCE = 8, PROF_MSM_SUMS = 9,
+               PROF_INPUTS = 10, PROF_ASSEMBLE = 11, PROF_ALL_TAGS = 12 };
 void prof_count_launches(uint64_t n);
 uint64_t prof_launches();
 bool prof_enabled();
@@ -58,9 +60,41 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
 };
 
-// Scratch for one MSM in flight (one per stream).
+// Scratch for one MSM in flight (one per stream).  The latency-bound tail of an MSM (oversized-bucket
+// merge, bucket reduction, window sums: few blocks, long dependent chains) is enqueued on `tail`, a
+// highest-priority stream, so its blocks are dispatched ahead of the thousands of queued accumulation
+// blocks of whatever bulk kernel shares the GPU; ordering with the caller's stream is kept by events.
 struct MsmWorkspace {
   DevBuf hist, off, cur, sorted, chunk_sums, buckets, tasks, obuckets, partial, mid, groups, windows, ctr, perm, bins;
+  cudaStream_t tail = nullptr;
+  cudaEvent_t e_fwd = nullptr, e_back = nullptr;
+  void ensure_tail() {
+    if (tail) return;
+    int lo = 0, hi = 0;
+    B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi is the numerically lowest = greatest priority
+    B200_CUDA(cudaStreamCreateWithPriority(&tail, cudaStreamNonBlocking, hi));
+    B200_CUDA(cudaEventCreateWithFlags(&e_fwd, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&e_back, cudaEventDisableTiming));
+  }
+  // work enqueued on `tail` after hop_to_tail(s) runs after everything already in s; hop_back makes s wait for it
+  void hop_to_tail(cudaStream_t s) {
+    ensure_tail();
+    B200_CUDA(cudaEventRecord(e_fwd, s));
+    B200_CUDA(cudaStreamWaitEvent(tail, e_fwd, 0));
+  }
+  void hop_back(cudaStream_t s, bool join) {   // !join: only mark the end of the tail (see wait_tail)
+    B200_CUDA(cudaEventRecord(e_back, tail));
+    if (join) B200_CUDA(cudaStreamWaitEvent(s, e_back, 0));   // (s may be the legacy default stream, 0)
+  }
+  void wait_tail(cudaStream_t s) { B200_CUDA(cudaStreamWaitEvent(s, e_back, 0)); }
+  MsmWorkspace() = default;
+  MsmWorkspace(const MsmWorkspace&) = delete;
+  MsmWorkspace& operator=(const MsmWorkspace&) = delete;
+  ~MsmWorkspace() {
+    if (tail) cudaStreamDestroy(tail);
+    if (e_fwd) cudaEventDestroy(e_fwd);
+    if (e_back) cudaEventDestroy(e_back);
+  }
 };
 
 // A base-point set with its precomputed window multiples resident in HBM ("table mode", msm_plan.h)
@@ -132,9 +166,11 @@ struct CurveBackend {
 
   // --- MSM: device pointers, result (one XYZZ point) written to d_out; fully asynchronous on `s`
   // d_index_map (optional): scalar i multiplies points[map[i]]; map[i] == 0xffffffff skips scalar i
+  // join = false: `s` does not wait for the MSM's latency-bound tail (which runs on ws.tail); the result is
+  // ready for any stream that calls ws.wait_tail(stream)
   virtual void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out_xyzz,
                    MsmWorkspace& ws, cudaStream_t s, int c_override, MsmStats* stats,
-                   const uint32_t* d_index_map = nullptr, const MsmBases* bases = nullptr) = 0;
+                   const uint32_t* d_index_map = nullptr, const MsmBases* bases = nullptr, bool join = true) = 0;
   // Shared-scalar MSMs (table mode): ONE digit/sort pass over `n` scalars feeds up to 4 base sets, set j
   // taking point maps[j][i] for scalar i (0xffffffff = skip).  msm_reduce then accumulates and reduces
   // `count` consecutive sets (their tables in `bases`, all of `group`) into `count` XYZZ results; a G1 and a
@@ -142,7 +178,7 @@ struct CurveBackend {
   virtual void msm_sort(const void* d_scalars, uint64_t n, const MsmBases* const* bases, const uint32_t* const* maps,
                         int nsets, MsmWorkspace& ws, cudaStream_t s, MsmSorted& out) = 0;
   virtual void msm_reduce(int group, const MsmSorted& so, int first_set, int count, const MsmBases* const* bases,
-                          void* d_out_xyzz, MsmWorkspace& ws, cudaStream_t s) = 0;
+                          void* d_out_xyzz, MsmWorkspace& ws, cudaStream_t s, bool join = true) = 0;
   // window width the cost model picks for a table-mode base set of npts points
   virtual int table_window(uint64_t npts) const = 0;
   // precompute T_j[i] = 2^(c j) P_i for a base set (window_bits = 0: cost model)

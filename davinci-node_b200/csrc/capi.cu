@@ -23,6 +23,7 @@ std::atomic<bool> g_prof_on{false};
 struct ProfRec {
   int tag;
   cudaEvent_t e0, e1;
+  cudaStream_t stream;
 };
 std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
@@ -32,7 +33,7 @@ uint64_t prof_launches() { return g_launch_count.load(); }
 bool prof_enabled() { return g_prof_on.load(); }
 int prof_begin(int tag, cudaStream_t s) {
   if (!g_prof_on.load()) return -1;
-  ProfRec r{tag, nullptr, nullptr};
+  ProfRec r{tag, nullptr, nullptr, s};
   if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
   cudaEventRecord(r.e0, s);
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -512,7 +513,7 @@ int b200_profile_collect(double ms_out[5], uint64_t count_out[5]) {
     }
     for (auto& r : g_prof) {
       float ms = 0;
-      if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      if (r.tag < PROF_TAGS && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
         ms_out[r.tag] += ms;
         count_out[r.tag]++;
       }
@@ -520,6 +521,38 @@ int b200_profile_collect(double ms_out[5], uint64_t count_out[5]) {
       cudaEventDestroy(r.e1);
     }
     g_prof.clear();
+  });
+}
+
+// Timeline of every instrumented phase since b200_profile_enable(1): 4 doubles per record
+// [tag, stream ordinal, start ms, end ms] relative to the earliest start.  Synchronises; does not clear.
+int b200_profile_timeline(double* out, uint64_t cap_records, uint64_t* n_out) {
+  return guarded([&] {
+    B200_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    *n_out = 0;
+    if (g_prof.empty()) return;
+    std::vector<cudaStream_t> streams;
+    std::vector<double> rel(g_prof.size() * 2);
+    double lo = 0;
+    for (size_t i = 0; i < g_prof.size(); i++) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, g_prof[0].e0, g_prof[i].e0);
+      cudaEventElapsedTime(&b, g_prof[0].e0, g_prof[i].e1);
+      rel[2 * i] = a;
+      rel[2 * i + 1] = b;
+      lo = std::min<double>(lo, a);
+    }
+    for (size_t i = 0; i < g_prof.size() && *n_out < cap_records; i++) {
+      size_t k = 0;
+      while (k < streams.size() && streams[k] != g_prof[i].stream) k++;
+      if (k == streams.size()) streams.push_back(g_prof[i].stream);
+      double* o = out + 4 * (*n_out)++;
+      o[0] = g_prof[i].tag;
+      o[1] = (double)k;
+      o[2] = rel[2 * i] - lo;
+      o[3] = rel[2 * i + 1] - lo;
+    }
   });
 }
 

@@ -255,6 +255,7 @@ void msm_sort_launch(const void* d_scalars, const MsmPlan& pl, const MsmSets& se
   if (nchunks > 1024) throw std::runtime_error("msm: too many buckets per array");
   uint32_t* chunk_sums = (uint32_t*)ws.chunk_sums.get(((uint64_t)pl.bwin * nchunks + pl.bwin) * 4);
   uint32_t* totals = chunk_sums + (uint64_t)pl.bwin * nchunks;
+  const int tok_sort = prof_begin(PROF_MSM_SORT, s);
   B200_CUDA(cudaMemsetAsync(hist, 0, total_b * 4, s));
   const auto* sc = reinterpret_cast<const typename Fr::El*>(d_scalars);
   const unsigned sblocks = (unsigned)((pl.n + 255) / 256);
@@ -262,6 +263,7 @@ void msm_sort_launch(const void* d_scalars, const MsmPlan& pl, const MsmSets& se
   k_msm_scan_sums<<<dim3(nchunks, pl.bwin), kScanThreads, 0, s>>>(hist, pl, chunk_sums);
   k_msm_scan<<<dim3(nchunks, pl.bwin), kScanThreads, 0, s>>>(hist, pl, chunk_sums, off, cur, totals);
   k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, sets);
+  prof_end(tok_sort, s);
   prof_count_launches(4);
   B200_CUDA(cudaGetLastError());
   out.pl = pl;
@@ -274,7 +276,8 @@ void msm_sort_launch(const void* d_scalars, const MsmPlan& pl, const MsmSets& se
 // ---- stage 2: bucket accumulation + reduction of `pl.bwin` bucket arrays -> d_out (one XYZZ point in
 // windowed mode, one per base set in table mode)
 template <class F, int GROUP>
-void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmWorkspace& ws, cudaStream_t s) {
+void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmWorkspace& ws, cudaStream_t s,
+                       bool join) {
   using Pt = XYZZ<F>;
   const MsmPlan& pl = so.pl;
   const uint64_t total_b = (uint64_t)pl.bwin * pl.nb;
@@ -295,6 +298,7 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   uint32_t* perm = (uint32_t*)ws.perm.get(total_b * 4);
   uint32_t* bins = (uint32_t*)ws.bins.get(2 * kSizeBins * 4);   // [bins | cursor]
 
+  const int tok_sched = prof_begin(PROF_MSM_SCHED, s);
   B200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(OvfCounters), s));
   B200_CUDA(cudaMemsetAsync(bins, 0, 2 * kSizeBins * 4, s));
   // size-sorted bucket schedule
@@ -302,28 +306,41 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   k_msm_size_hist<<<szblocks, kSizeThreads, 0, s>>>(so.off, so.end, total_b, bins);
   k_msm_size_scan<<<1, kSizeBins, 0, s>>>(bins, bins + kSizeBins);
   k_msm_size_scatter<<<szblocks, kSizeThreads, 0, s>>>(so.off, so.end, total_b, bins + kSizeBins, perm);
+  prof_end(tok_sched, s);
   const int tok_acc = prof_begin(GROUP == 2 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1, s);
   k_msm_accumulate<F><<<(unsigned)((total_b + B200_ACC_THREADS - 1) / B200_ACC_THREADS), B200_ACC_THREADS, 0, s>>>(
       pts, so.sorted, so.off, so.end, perm, so.totals, pl, buckets, obuckets, ctr);
   prof_end(tok_acc, s);
+  // ---- latency-bound tail on the high-priority stream
+  ws.hop_to_tail(s);
+  cudaStream_t t = ws.tail;
   // oversized buckets: task list, partial sums, then a small-bucket merge and a two-level tree for big ones
-  k_msm_ovf_expand<<<148, 256, 0, s>>>(obuckets, ctr, pl, tasks);
+  const int tok_ovf = prof_begin(PROF_MSM_OVF, t);
+  k_msm_ovf_expand<<<148, 256, 0, t>>>(obuckets, ctr, pl, tasks);
   unsigned ovf_blocks = (unsigned)std::min<uint64_t>((pl.max_ovf + 127) / 128, 148 * 8);
-  k_msm_ovf_accumulate<F><<<ovf_blocks, 128, 0, s>>>(pts, so.sorted, pl, tasks, ctr, partial);
-  k_msm_ovf_merge_small<F><<<64, 64, 0, s>>>(obuckets, ctr, partial, buckets);
+  k_msm_ovf_accumulate<F><<<ovf_blocks, 128, 0, t>>>(pts, so.sorted, pl, tasks, ctr, partial);
+  k_msm_ovf_merge_small<F><<<64, 64, 0, t>>>(obuckets, ctr, partial, buckets);
   const size_t merge_smem = kOvfMergeThreads * sizeof(Pt);
-  k_msm_ovf_merge_l1<F><<<dim3(32, 64), kOvfMergeThreads, merge_smem, s>>>(obuckets, ctr, partial, mid);
-  k_msm_ovf_merge_l2<F><<<256, kOvfMergeThreads, merge_smem, s>>>(obuckets, ctr, mid, buckets);
+  k_msm_ovf_merge_l1<F><<<dim3(32, 64), kOvfMergeThreads, merge_smem, t>>>(obuckets, ctr, partial, mid);
+  k_msm_ovf_merge_l2<F><<<256, kOvfMergeThreads, merge_smem, t>>>(obuckets, ctr, mid, buckets);
+  prof_end(tok_ovf, t);
   size_t red_smem = kReduceThreads * sizeof(Pt);
-  k_msm_bucket_reduce<F><<<(pl.bwin * ngroups + 63) / 64, 64, 0, s>>>(buckets, pl, groups);
+  const int tok_br = prof_begin(PROF_MSM_BUCKET_REDUCE, t);
+  k_msm_bucket_reduce<F><<<(pl.bwin * ngroups + 63) / 64, 64, 0, t>>>(buckets, pl, groups);
+  prof_end(tok_br, t);
+  const int tok_sums = prof_begin(PROF_MSM_SUMS, t);
   if (two_level) {
-    k_msm_slice_sum<F><<<pl.bwin * kSlices, kReduceThreads, red_smem, s>>>(groups, ngroups / kSlices, mids);
-    k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, s>>>(mids, kSlices, windows);
+    k_msm_slice_sum<F><<<pl.bwin * kSlices, kReduceThreads, red_smem, t>>>(groups, ngroups / kSlices, mids);
+    k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, t>>>(mids, kSlices, windows);
   } else {
-    k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, s>>>(groups, ngroups, windows);
+    k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, t>>>(groups, ngroups, windows);
   }
-  k_msm_horner<F><<<1, 32, 0, s>>>(windows, pl, (Pt*)d_out);
-  prof_count_launches(two_level ? 13 : 12);
+  k_msm_horner<F><<<1, 32, 0, t>>>(windows, pl, (Pt*)d_out);
+  prof_end(tok_sums, t);
+  // join: the caller's stream waits for the tail; otherwise the result is ready when ws.e_back fires
+  // (ws.wait_tail(other_stream)) and the caller's stream may run ahead with independent bulk work
+  ws.hop_back(s, join);
+  prof_count_launches(two_level ? 16 : 15);
   B200_CUDA(cudaGetLastError());
 }
 
@@ -354,13 +371,17 @@ struct CurveImpl : CurveBackend {
 
   void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out, MsmWorkspace& ws,
            cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map,
-           const MsmBases* bases) override {
+           const MsmBases* bases, bool join) override {
     if (bases && bases->group != group) throw std::runtime_error("msm: base tables belong to the other group");
     if (n >= (1ull << 31)) throw std::runtime_error("msm: n must be < 2^31");
     MsmPlan pl = bases ? make_msm_plan_table(n, Fr::BITS, bases->c, bases->npts) : make_msm_plan(n, Fr::BITS, c_override);
     if (stats) *stats = MsmStats{pl.c, pl.nwin, pl.nb, pl.task, pl.group};
     if (n == 0) {
       B200_CUDA(cudaMemsetAsync(d_out, 0, xyzz_bytes(group), s));
+      if (!join) {   // keep the contract: the result is ready when the tail event fires
+        ws.hop_to_tail(s);
+        ws.hop_back(s, false);
+      }
       return;
     }
     MsmSets sets{};
@@ -371,18 +392,18 @@ struct CurveImpl : CurveBackend {
     MsmSorted so;
     const int tok_total = prof_begin(group == 2 ? PROF_MSM_TOTAL_G2 : PROF_MSM_TOTAL_G1, s);
     msm_sort_launch<Fr>(d_scalars, pl, sets, ws, s, so);
-    reduce_dispatch(group, so, pts, d_out, ws, s);
+    reduce_dispatch(group, so, pts, d_out, ws, s, join);
     prof_end(tok_total, s);
   }
 
   void reduce_dispatch(int group, const MsmSorted& so, const MsmPts& pts, void* d_out, MsmWorkspace& ws,
-                       cudaStream_t s) {
+                       cudaStream_t s, bool join = true) {
     if (group == 1) {
       msm_set_smem_attrs<G1F>();
-      msm_reduce_launch<G1F, 1>(so, pts, d_out, ws, s);
+      msm_reduce_launch<G1F, 1>(so, pts, d_out, ws, s, join);
     } else {
       msm_set_smem_attrs<G2F>();
-      msm_reduce_launch<G2F, 2>(so, pts, d_out, ws, s);
+      msm_reduce_launch<G2F, 2>(so, pts, d_out, ws, s, join);
     }
   }
 
@@ -402,7 +423,7 @@ struct CurveImpl : CurveBackend {
   }
 
   void msm_reduce(int group, const MsmSorted& so, int first_set, int count, const MsmBases* const* bases,
-                  void* d_out, MsmWorkspace& ws, cudaStream_t s) override {
+                  void* d_out, MsmWorkspace& ws, cudaStream_t s, bool join) override {
     if (!so.pl.table || first_set < 0 || count < 1 || first_set + count > so.pl.bwin)
       throw std::runtime_error("msm_reduce: bad set range");
     MsmSorted sub = so;
@@ -416,7 +437,7 @@ struct CurveImpl : CurveBackend {
       if (bases[j]->group != group) throw std::runtime_error("msm_reduce: base tables belong to the other group");
       pts.p[j] = bases[j]->tables.p;
     }
-    reduce_dispatch(group, sub, pts, d_out, ws, s);
+    reduce_dispatch(group, sub, pts, d_out, ws, s, join);
   }
 
   int table_window(uint64_t npts) const override { return msm_table_window(npts, Fr::BITS); }

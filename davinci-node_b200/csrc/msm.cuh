@@ -417,17 +417,24 @@ k_msm_size_scatter(const uint32_t* __restrict__ off, const uint32_t* __restrict_
   }
 }
 
-template <class F>
 #ifndef B200_ACC_NO_LOCKSTEP
 #define B200_ACC_LOCKSTEP 1   // measured: -5% (G1) / -8% (G2) accumulate time at 128 threads, 3 blocks per SM
 #endif
 #ifndef B200_ACC_MIN_BLOCKS
 #define B200_ACC_MIN_BLOCKS 3
 #endif
+#ifndef B200_ACC_MIN_BLOCKS_BIG
+#define B200_ACC_MIN_BLOCKS_BIG 3   // coordinate fields of >= 96 bytes (Fp2 over 377/381-bit primes, BW6-761 Fp)
+#endif
 #ifndef B200_ACC_THREADS
 #define B200_ACC_THREADS 128
 #endif
-__global__ void __launch_bounds__(B200_ACC_THREADS, B200_ACC_MIN_BLOCKS)
+template <class F>
+struct AccCfg {
+  static constexpr int kMinBlocks = sizeof(typename F::El) >= 96 ? B200_ACC_MIN_BLOCKS_BIG : B200_ACC_MIN_BLOCKS;
+};
+template <class F>
+__global__ void __launch_bounds__(B200_ACC_THREADS, AccCfg<F>::kMinBlocks)
 k_msm_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
                  const uint32_t* __restrict__ end, const uint32_t* __restrict__ perm,
                  const uint32_t* __restrict__ totals, MsmPlan pl, XYZZ<F>* __restrict__ buckets,

@@ -7,6 +7,7 @@
 #include "prover.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace b200 {
@@ -34,12 +35,25 @@ void upload(DevBuf& buf, const void* src, size_t bytes, cudaStream_t s) {
   if (bytes) B200_CUDA(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, s));
 }
 
+// every stream of the slot is idle afterwards (the slot's buffers may be reused by the next proof)
+void sync_bulk(PkSlot& S) {
+  for (auto& s : S.st) B200_CUDA(cudaStreamSynchronize(s));
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------ PkInstance
 PkSlot::PkSlot(int dev) : device(dev) {
   DeviceScope ds(dev);
-  for (auto& s : st) B200_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  // st[0] bulk kernels, st[1] input copies, st[2] / st[3] extra bulk streams (B200_BULK_STREAMS=3);
+  // `hi` runs the single-thread proof assembly at the highest priority
+  int lo = 0, hi_p = 0;
+  B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi_p));
+  B200_CUDA(cudaStreamCreateWithPriority(&st[0], cudaStreamNonBlocking, lo));
+  B200_CUDA(cudaStreamCreateWithPriority(&st[1], cudaStreamNonBlocking, lo));
+  B200_CUDA(cudaStreamCreateWithPriority(&st[2], cudaStreamNonBlocking, lo));
+  B200_CUDA(cudaStreamCreateWithPriority(&st[3], cudaStreamNonBlocking, lo));
+  B200_CUDA(cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, hi_p));
   for (auto& e : ev) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 }
 
@@ -47,6 +61,7 @@ PkSlot::~PkSlot() {
   cudaSetDevice(device);
   for (auto& s : st)
     if (s) cudaStreamDestroy(s);
+  if (hi) cudaStreamDestroy(hi);
   for (auto& e : ev)
     if (e) cudaEventDestroy(e);
 }
@@ -149,7 +164,10 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
       B200_CUDA(cudaStreamSynchronize(s));   // staging buffer is reused by the next base set
     };
     // the wire-indexed keys share one digit/sort pass per proof, hence one window width
-    const int cw = cb->table_window(std::max({d.g1_A.len + 2, d.g1_B.len + 2, d.g1_K.len + 1}));
+    int cw = cb->table_window(std::max({d.g1_A.len + 2, d.g1_B.len + 2, d.g1_K.len + 1}));
+    if (const char* e = std::getenv("B200_WIRE_WINDOW")) {   // tuning knob: window width of the wire-indexed keys
+      if (std::atoi(e) >= 4 && std::atoi(e) <= 22) cw = std::atoi(e);
+    }
     put_tables(in->tA, 1, d.g1_A, g1b, d.g1_delta, d.g1_alpha, cw);
     put_tables(in->tB1, 1, d.g1_B, g1b, d.g1_delta, d.g1_beta, cw);
     put_tables(in->tB2, 2, d.g2_B, g2b, d.g2_delta, d.g2_beta, cw);
@@ -225,94 +243,116 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   if (in.nb_commitments != commit_n.size()) throw std::runtime_error("nb_commitments mismatch with proving key");
   if (!in.r || !in.s) throw std::runtime_error("r / s missing");
   const cudaMemcpyKind kind = inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  cudaStream_t s0 = S.st[0], s1 = S.st[1], s2 = S.st[2];
+  // Streams.  sc: input copies.  Bulk (throughput-bound) kernels - sorts, bucket accumulation, NTT passes - go to
+  // ONE stream per proof by default (sb == sw == sg): two different accumulation kernels sharing an SM evict each
+  // other's instruction-cache-sized loop bodies, so they are better run back to back.  B200_BULK_STREAMS=3 restores
+  // three concurrent bulk streams.  Every MSM's latency-bound tail runs on its workspace's high-priority stream
+  // and is only joined by the assembly.
+  static const bool three_bulk = [] {
+    const char* e = std::getenv("B200_BULK_STREAMS");
+    return e && std::atoi(e) == 3;
+  }();
+  cudaStream_t sc = S.st[1], sb = S.st[0];
+  cudaStream_t sw = three_bulk ? S.st[2] : sb;    // wire-indexed G1 MSMs
+  cudaStream_t sg = three_bulk ? S.st[3] : sb;    // G2 MSM
   uint8_t* W = (uint8_t*)S.W.p;
   uint8_t* a = (uint8_t*)S.a.p;
   uint8_t* b = (uint8_t*)S.b.p;
   uint8_t* c = (uint8_t*)S.c.p;
 
-  // ---- inputs (s0): wire vector first so the A / B MSMs can start while a, b, c are still arriving
-  B200_CUDA(cudaMemcpyAsync(W, in.wires.ptr, m * frb, kind, s0));
+  // ---- inputs (sc): wire vector first so the wire-indexed MSMs can start while a, b, c are still arriving
+  int tok_in = prof_begin(PROF_INPUTS, sc);
+  B200_CUDA(cudaMemcpyAsync(W, in.wires.ptr, m * frb, kind, sc));
   uint8_t* rs_in = (uint8_t*)S.rs.p;
-  B200_CUDA(cudaMemcpyAsync(rs_in, in.r, frb, kind, s0));
-  B200_CUDA(cudaMemcpyAsync(rs_in + frb, in.s, frb, kind, s0));
-  cb->prep_rs(rs_in, rs_in + frb, W + m * frb, s0);
-  B200_CUDA(cudaEventRecord(S.ev[0], s0));
-
-  uint8_t* mo = (uint8_t*)S.msm_out.p;   // [ar, bs1, k, z, pok] G1 then bs2 G2
-  uint8_t *o_ar = mo, *o_bs1 = mo + x1, *o_k = mo + 2 * x1, *o_z = mo + 3 * x1, *o_pok = mo + 4 * x1,
-          *o_bs2 = mo + 5 * x1;
-
-  // ---- s1: ONE digit/sort pass over W_ext feeds the A, B and K keys; Ar, Bs1 and the wire part of Krs are
-  //         reduced together in G1.   s2: Bs (G2) reduces the B set of the same sorted data.
-  B200_CUDA(cudaStreamWaitEvent(s1, S.ev[0], 0));
-  {
-    const MsmBases* sets[3] = {&I.tA, &I.tB1, &I.tK};
-    const uint32_t* maps[3] = {(const uint32_t*)I.mapA.p, (const uint32_t*)I.mapB.p, (const uint32_t*)I.mapK.p};
-    MsmSorted so;
-    cb->msm_sort(W, m + 4, sets, maps, 3, S.ws[1], s1, so);
-    B200_CUDA(cudaEventRecord(S.ev[3], s1));
-    cb->msm_reduce(1, so, 0, 3, sets, o_ar, S.ws[1], s1);   // -> o_ar, o_bs1, o_k (contiguous)
-    B200_CUDA(cudaEventRecord(S.ev[1], s1));
-    B200_CUDA(cudaStreamWaitEvent(s2, S.ev[3], 0));
-    const MsmBases* g2set[1] = {&I.tB2};
-    cb->msm_reduce(2, so, 1, 1, g2set, o_bs2, S.ws[2], s2);
-    B200_CUDA(cudaEventRecord(S.ev[2], s2));
-  }
-
-  // ---- s0: quotient, Z MSM, proof of knowledge
+  B200_CUDA(cudaMemcpyAsync(rs_in, in.r, frb, kind, sc));
+  B200_CUDA(cudaMemcpyAsync(rs_in + frb, in.s, frb, kind, sc));
+  cb->prep_rs(rs_in, rs_in + frb, W + m * frb, sc);
+  prof_end(tok_in, sc);
+  B200_CUDA(cudaEventRecord(S.ev[0], sc));
+  tok_in = prof_begin(PROF_INPUTS, sc);
   const uint64_t nc = in.a.len;
   if (nc < n) {
-    B200_CUDA(cudaMemsetAsync(a + nc * frb, 0, (n - nc) * frb, s0));
-    B200_CUDA(cudaMemsetAsync(b + nc * frb, 0, (n - nc) * frb, s0));
-    B200_CUDA(cudaMemsetAsync(c + nc * frb, 0, (n - nc) * frb, s0));
+    B200_CUDA(cudaMemsetAsync(a + nc * frb, 0, (n - nc) * frb, sc));
+    B200_CUDA(cudaMemsetAsync(b + nc * frb, 0, (n - nc) * frb, sc));
+    B200_CUDA(cudaMemsetAsync(c + nc * frb, 0, (n - nc) * frb, sc));
   }
   if (nc) {
-    B200_CUDA(cudaMemcpyAsync(a, in.a.ptr, nc * frb, kind, s0));
-    B200_CUDA(cudaMemcpyAsync(b, in.b.ptr, nc * frb, kind, s0));
-    B200_CUDA(cudaMemcpyAsync(c, in.c.ptr, nc * frb, kind, s0));
+    B200_CUDA(cudaMemcpyAsync(a, in.a.ptr, nc * frb, kind, sc));
+    B200_CUDA(cudaMemcpyAsync(b, in.b.ptr, nc * frb, kind, sc));
+    B200_CUDA(cudaMemcpyAsync(c, in.c.ptr, nc * frb, kind, sc));
   }
-  cb->compute_h(I.dom, a, b, c, s0);
-  cb->msm(1, nullptr, a + z_offset * frb, nZ, o_z, S.ws[0], s0, 0, nullptr, nullptr, &I.tZ);
   bool have_pok = total_commit > 0 || !commit_n.empty();
+  uint8_t* cv = (uint8_t*)S.cvals.p;
   if (have_pok) {
-    uint8_t* cv = (uint8_t*)S.cvals.p;
     uint64_t off = 0;
     for (size_t i = 0; i < commit_n.size(); i++) {
       if (in.priv_committed[i].len != commit_n[i])
         throw std::runtime_error("private committed values: length mismatch with commitment key");
-      if (commit_n[i]) B200_CUDA(cudaMemcpyAsync(cv + off * frb, in.priv_committed[i].ptr, commit_n[i] * frb, kind, s0));
+      if (commit_n[i]) B200_CUDA(cudaMemcpyAsync(cv + off * frb, in.priv_committed[i].ptr, commit_n[i] * frb, kind, sc));
       if (i >= 1) {
         if (!in.fold_challenge) throw std::runtime_error("fold_challenge required with more than one commitment");
-        if (i == 1) B200_CUDA(cudaMemcpyAsync(S.chal.p, in.fold_challenge, frb, kind, s0));
-        // segment i is scaled by challenge^i : scale every later segment once per step
+        if (i == 1) B200_CUDA(cudaMemcpyAsync(S.chal.p, in.fold_challenge, frb, kind, sc));
       }
       off += commit_n[i];
     }
-    // scale segments [i..] by the challenge, for i = 1 .. k-1  => segment j picks up challenge^j
-    off = 0;
+  }
+  prof_end(tok_in, sc);
+  B200_CUDA(cudaEventRecord(S.ev[1], sc));
+
+  uint8_t* mo = (uint8_t*)S.msm_out.p;   // [ar, bs1, k, z, pok] G1 then bs2 G2
+  uint8_t *o_ar = mo, *o_z = mo + 3 * x1, *o_pok = mo + 4 * x1, *o_bs2 = mo + 5 * x1;
+
+  // ---- wire-indexed MSMs: ONE digit/sort pass over W_ext feeds the A, B and K keys; Ar, Bs1 and the wire part
+  //      of Krs are reduced together in G1, Bs (G2) reduces the B set of the same sorted data
+  B200_CUDA(cudaStreamWaitEvent(sw, S.ev[0], 0));
+  {
+    const MsmBases* sets[3] = {&I.tA, &I.tB1, &I.tK};
+    const uint32_t* maps[3] = {(const uint32_t*)I.mapA.p, (const uint32_t*)I.mapB.p, (const uint32_t*)I.mapK.p};
+    MsmSorted so;
+    cb->msm_sort(W, m + 4, sets, maps, 3, S.ws[1], sw, so);
+    if (sg != sw) {
+      B200_CUDA(cudaEventRecord(S.ev[2], sw));
+      B200_CUDA(cudaStreamWaitEvent(sg, S.ev[2], 0));
+    }
+    cb->msm_reduce(1, so, 0, 3, sets, o_ar, S.ws[1], sw, false);   // -> o_ar, o_bs1, o_k (contiguous)
+    const MsmBases* g2set[1] = {&I.tB2};
+    cb->msm_reduce(2, so, 1, 1, g2set, o_bs2, S.ws[2], sg, false);
+  }
+
+  // ---- quotient, Z MSM, proof of knowledge
+  B200_CUDA(cudaStreamWaitEvent(sb, S.ev[1], 0));
+  cb->compute_h(I.dom, a, b, c, sb);
+  cb->msm(1, nullptr, a + z_offset * frb, nZ, o_z, S.ws[0], sb, 0, nullptr, nullptr, &I.tZ, false);
+  if (have_pok) {
+    // segment i of the committed values is scaled by challenge^i: scale every later segment once per step
+    uint64_t off = 0;
     for (size_t i = 0; i < commit_n.size(); i++) {
-      if (i >= 1) cb->scale_vec(cv + off * frb, S.chal.p, total_commit - off, s0);
+      if (i >= 1) cb->scale_vec(cv + off * frb, S.chal.p, total_commit - off, sb);
       off += commit_n[i];
     }
-    cb->msm(1, nullptr, cv, total_commit, o_pok, S.ws[0], s0, 0, nullptr, nullptr, &I.tSigma);
+    cb->msm(1, nullptr, cv, total_commit, o_pok, S.ws[3], sb, 0, nullptr, nullptr, &I.tSigma, false);
   }
-  B200_CUDA(cudaStreamWaitEvent(s0, S.ev[1], 0));
-  B200_CUDA(cudaStreamWaitEvent(s0, S.ev[2], 0));
+  // ---- join every tail on the high-priority stream
+  cudaStream_t sh = S.hi;
+  S.ws[0].wait_tail(sh);
+  S.ws[1].wait_tail(sh);
+  S.ws[2].wait_tail(sh);
+  if (have_pok) S.ws[3].wait_tail(sh);
   if (d_partials) {
     // range-split mode: hand the raw partial sums back (layout of msm_out: 5 G1 XYZZ then 1 G2 XYZZ)
-    if (!have_pok) B200_CUDA(cudaMemsetAsync(o_pok, 0, x1, s0));
-    B200_CUDA(cudaMemcpyAsync(d_partials, mo, 5 * x1 + x2, cudaMemcpyDeviceToDevice, s0));
-    B200_CUDA(cudaStreamSynchronize(s0));
+    if (!have_pok) B200_CUDA(cudaMemsetAsync(o_pok, 0, x1, sh));
+    B200_CUDA(cudaMemcpyAsync(d_partials, mo, 5 * x1 + x2, cudaMemcpyDeviceToDevice, sh));
+    B200_CUDA(cudaStreamSynchronize(sh));
+    sync_bulk(S);
     return;
   }
 
   uint8_t* oa = (uint8_t*)S.out_aff.p;   // ar, krs, pok (G1), bs (G2)
   AssembleArgs aa{};
   aa.ar_msm = o_ar;
-  aa.bs1_msm = o_bs1;
+  aa.bs1_msm = mo + x1;
   aa.bs2_msm = o_bs2;
-  aa.k_msm = o_k;
+  aa.k_msm = mo + 2 * x1;
   aa.z_msm = o_z;
   aa.pok_msm = have_pok ? o_pok : nullptr;
   aa.rs = W + m * frb;
@@ -321,13 +361,18 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   aa.out_krs = oa + g1b;
   aa.out_pok = oa + 2 * g1b;
   aa.out_bs = oa + 3 * g1b;
-  cb->assemble(aa, s0);
+  // the assembly is two single-thread scalar multiplications: it runs on the high-priority stream so it is
+  // not queued behind the accumulation blocks of the other proofs in flight
+  const int tok_asm = prof_begin(PROF_ASSEMBLE, S.hi);
+  cb->assemble(aa, S.hi);
+  prof_end(tok_asm, S.hi);
   const cudaMemcpyKind back = inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  B200_CUDA(cudaMemcpyAsync(out.ar, oa, g1b, back, s0));
-  B200_CUDA(cudaMemcpyAsync(out.krs, oa + g1b, g1b, back, s0));
-  if (have_pok && out.pok) B200_CUDA(cudaMemcpyAsync(out.pok, oa + 2 * g1b, g1b, back, s0));
-  B200_CUDA(cudaMemcpyAsync(out.bs, oa + 3 * g1b, g2b, back, s0));
-  B200_CUDA(cudaStreamSynchronize(s0));
+  B200_CUDA(cudaMemcpyAsync(out.ar, oa, g1b, back, S.hi));
+  B200_CUDA(cudaMemcpyAsync(out.krs, oa + g1b, g1b, back, S.hi));
+  if (have_pok && out.pok) B200_CUDA(cudaMemcpyAsync(out.pok, oa + 2 * g1b, g1b, back, S.hi));
+  B200_CUDA(cudaMemcpyAsync(out.bs, oa + 3 * g1b, g2b, back, S.hi));
+  B200_CUDA(cudaStreamSynchronize(S.hi));
+  sync_bulk(S);
 }
 
 // commitment i = sum_j values[j] * Basis_i[j]   (called from the solver hint, synchronous)

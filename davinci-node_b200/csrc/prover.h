@@ -16,10 +16,11 @@ namespace b200 {
 struct PkSlot {
   int device;
   std::mutex mu;
-  cudaStream_t st[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t st[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t hi = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   DevBuf W, a, b, c, rs, cvals, chal, msm_out, tmp, out_aff;
-  MsmWorkspace ws[3];
+  MsmWorkspace ws[4];   // [0] Z, [1] wire-indexed G1 sets (+ the shared sort), [2] G2, [3] PoK
   explicit PkSlot(int dev);
   ~PkSlot();
 };

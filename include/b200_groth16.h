@@ -189,6 +189,10 @@ B200_API uint64_t b200_launch_count(void);
  * 3 = whole G1 MSM, 4 = whole G2 MSM.  collect() synchronises, sums ms / launch counts per tag, clears. */
 B200_API int b200_profile_enable(int on);
 B200_API int b200_profile_collect(double ms_out[5], uint64_t count_out[5]);
+/* every instrumented phase recorded since b200_profile_enable(1), 4 doubles per record: [tag, stream ordinal,
+ * start ms, end ms].  Further tags: 5 digit/sort, 6 bucket schedule, 7 oversized buckets, 8 bucket reduction,
+ * 9 window sums, 10 input copies, 11 proof assembly.  Synchronises the device; does not clear. */
+B200_API int b200_profile_timeline(double* out, uint64_t cap_records, uint64_t* n_out);
 
 /* ---- debug / parity entry points (device pointers; element-wise over n items) ---------------
  * field: 0 = Fp, 1 = Fr, 2 = Fp2 ; op: 0 add, 1 sub, 2 mul, 3 sqr, 4 from_mont, 5 to_mont, 6 inv, 7 neg */

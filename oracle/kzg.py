@@ -61,3 +61,76 @@ def blob_to_commitment(blob: bytes, lagrange_points) -> bytes:
     logn = n.bit_length() - 1
     pts = [lagrange_points[N.bitrev(i, logn)] for i in range(n)]
     return g1_compress(cx.G1.msm(pts, vals))
+
+
+# ----------------------------------------------------------------------------- opening proofs
+# Restates go-ethereum `kzg4844.ComputeProof` / `ComputeBlobProof` (called at
+# /root/reference/types/blobs.go:111-134) = EIP-4844 `compute_kzg_proof_impl` / `compute_blob_kzg_proof`
+# (consensus-specs deneb/polynomial-commitments.md): the blob is the polynomial's evaluations over the
+# 4096th roots of unity in bit-reversed order; the proof commits to q(X) = (p(X) - p(z)) / (X - z) in the same
+# evaluation basis.
+PRIMITIVE_ROOT_2_32 = 10238227357739495823651030575849232062558860180284477541189508159991286009131  # barycentric.go:52
+FIAT_SHAMIR_PROTOCOL_DOMAIN = b"FSBLOBVERIFY_V1_"
+
+
+def roots_of_unity_brp(n):
+    r = P.BLS12_381.r
+    logn = n.bit_length() - 1
+    w = pow(PRIMITIVE_ROOT_2_32, 1 << (32 - logn), r)
+    nat = [1] * n
+    for i in range(1, n):
+        nat[i] = nat[i - 1] * w % r
+    return [nat[N.bitrev(i, logn)] for i in range(n)]
+
+
+def evaluate_in_evaluation_form(poly, z, roots):
+    r = P.BLS12_381.r
+    n = len(poly)
+    if z in roots:
+        return poly[roots.index(z)]
+    acc = 0
+    for pi, wi in zip(poly, roots):
+        acc += pi * wi % r * pow((z - wi) % r, -1, r)
+    return acc % r * ((pow(z, n, r) - 1) % r) % r * pow(n, -1, r) % r
+
+
+def quotient_evaluations(poly, z, roots):
+    """(q evaluations, y): q_i = (p_i - y) / (w_i - z); the in-domain case follows the spec's
+    compute_quotient_eval_within_domain."""
+    r = P.BLS12_381.r
+    y = evaluate_in_evaluation_form(poly, z, roots)
+    q = [0] * len(poly)
+    for i, (pi, wi) in enumerate(zip(poly, roots)):
+        if wi == z:
+            acc = 0
+            for pj, wj in zip(poly, roots):
+                if wj == z:
+                    continue
+                acc += (pj - y) % r * wj % r * pow(z * (z - wj) % r, -1, r)
+            q[i] = acc % r
+        else:
+            q[i] = (pi - y) % r * pow((wi - z) % r, -1, r) % r
+    return q, y
+
+
+def compute_proof(blob: bytes, z: int, lagrange_points):
+    """-> (48-byte proof, claimed value y as int).  lagrange_points in SRS-file (natural) order."""
+    cx = C.ctx("bls12_381")
+    vals = blob_scalars(blob)
+    n = len(vals)
+    logn = n.bit_length() - 1
+    roots = roots_of_unity_brp(n)
+    q, y = quotient_evaluations(vals, z % P.BLS12_381.r, roots)
+    pts = [lagrange_points[N.bitrev(i, logn)] for i in range(n)]
+    return g1_compress(cx.G1.msm(pts, q)), y
+
+
+def compute_challenge(blob: bytes, commitment: bytes) -> int:
+    import hashlib
+    n = len(blob) // 32
+    data = FIAT_SHAMIR_PROTOCOL_DOMAIN + n.to_bytes(16, "big") + blob + commitment
+    return int.from_bytes(hashlib.sha256(data).digest(), "big") % P.BLS12_381.r
+
+
+def compute_blob_proof(blob: bytes, commitment: bytes, lagrange_points) -> bytes:
+    return compute_proof(blob, compute_challenge(blob, commitment), lagrange_points)[0]

@@ -49,9 +49,15 @@ class Prog:
         return d
 
     # --- interpreter (PTX semantics, CC.CF modelled explicitly)
-    def run(self, in_vals):
+    def run(self, in_vals, strict=False):
+        """Interpret with PTX semantics.  strict=True additionally raises when an addition WITHOUT a carry-out
+        (.cc) overflows, i.e. when the program would silently drop a carry."""
         reg = dict(zip(self.inputs, in_vals))
         cf = 0
+
+        def lost(t, opc):
+            if strict and (t >> 32):
+                raise OverflowError("carry dropped by %s in %s" % (opc, self.name))
 
         def v(x):
             return x & MASK if isinstance(x, int) else reg[x]
@@ -65,6 +71,8 @@ class Prog:
                 t = v(s[0]) + v(s[1]) + (cf if cin else 0)
                 if cc_out:
                     cf = t >> 32
+                else:
+                    lost(t, opc)
                 reg[d] = t & MASK
             elif base in ("sub", "subc"):
                 t = v(s[0]) - v(s[1]) - (cf if cin else 0)
@@ -77,6 +85,8 @@ class Prog:
                 t = part + v(s[2]) + (cf if cin else 0)
                 if cc_out:
                     cf = t >> 32
+                else:
+                    lost(t, opc)
                 reg[d] = t & MASK
             elif base == "mul":
                 prod = v(s[0]) * v(s[1])
@@ -188,18 +198,40 @@ def _reduce_row(P, X, Y, p_l, m0):
     """X (pos 0..n-1) / Y (pos 1..n): add m*p so that X[0] becomes 0."""
     n = len(X)
     m = P.tmp()
-    # m0 == 2^32-1 would let ptxas rewrite m = -X[0] and fold the negation into the modulus
-    # immediates of the lo half only, which blocks IMAD.WIDE fusion - keep it opaque instead.
-    P.op("mul.lo", m, X[0], "m0r" if (m0 == MASK and "m0r" in P.inputs) else m0)
+    unit = m0 == MASK and p_l[0] == 1 and "zr" in P.inputs
+    if unit:
+        # p = 1 mod 2^32 (BLS12-377 fp / fr, BLS12-381 fr): m = -X[0] and the first column is X[0] + m = 0 with
+        # carry (X[0] != 0) - both are plain integer adds on the ALU pipe instead of an IMAD and an IMAD.HI on the
+        # (binding) multiplier pipe.  The zero comes from the constant bank so ptxas cannot fold the negation
+        # into the other columns' multiplies (which would break their IMAD.WIDE fusion).
+        P.op("sub", m, "zr", X[0])
+    else:
+        # m0 == 2^32-1 would let ptxas rewrite m = -X[0] and fold the negation into the modulus
+        # immediates of the lo half only, which blocks IMAD.WIDE fusion - keep it opaque instead.
+        P.op("mul.lo", m, X[0], "m0r" if (m0 == MASK and "m0r" in P.inputs) else m0)
     # odd limbs of p into Y
     for j in range(0, n, 2):
         P.op("mad.lo.cc" if j == 0 else "madc.lo.cc", Y[j], m, p_l[j + 1], Y[j])
         P.op("madc.hi.cc" if j + 2 < n else "madc.hi", Y[j + 1], m, p_l[j + 1], Y[j + 1])
     # even limbs of p into X
     for j in range(0, n, 2):
+        if unit and j == 0:
+            P.op("add.cc", X[0], X[0], m)
+            P.op("addc.cc", X[1], X[1], 0)
+            continue
         P.op("mad.lo.cc" if j == 0 else "madc.lo.cc", X[j], m, p_l[j], X[j])
         P.op("madc.hi.cc", X[j + 1], m, p_l[j], X[j + 1])
     P.op("addc", Y[n - 1], Y[n - 1], 0)
+
+
+def _opaque_inputs(p, n):
+    """extra inputs read through the constant bank: the opaque zero (unit-low-limb moduli) or the opaque M0"""
+    m0 = (-pow(p, -1, 1 << 32)) & MASK
+    # opt-in (B200_GEN_UNIT=1): measured on B200 the binding resource is the IMAD.WIDE count, which this
+    # variant does not change (the IMAD / IMAD.HI it removes issue beside the wide MACs), so it is off by default
+    if m0 == MASK and (p & MASK) == 1 and os.environ.get("B200_GEN_UNIT"):
+        return ["zr"]
+    return ["m0r"] if m0 == MASK else []
 
 
 def prog_mul(n, p, b_is_a=False):
@@ -208,7 +240,7 @@ def prog_mul(n, p, b_is_a=False):
     A = ["a%d" % i for i in range(n)]
     B = A if b_is_a else ["b%d" % i for i in range(n)]
     m0 = (-pow(p, -1, 1 << 32)) & MASK
-    extra = ["m0r"] if m0 == MASK else []
+    extra = _opaque_inputs(p, n)
     P = Prog("sqr" if b_is_a else "mul", (A if b_is_a else A + B) + extra, n)
     p_l = limbs(p, n)
     X = [P.tmp() for _ in range(n)]
@@ -243,11 +275,101 @@ def prog_mul(n, p, b_is_a=False):
     return P
 
 
+def _mont_rows(P, X, Y, p_l, m0, n):
+    """n Montgomery reduction rows over the single-width value held in X (+ Y = 0): returns the n-limb
+    list T = (X + q p) / R  (< p + 1), not yet conditionally reduced."""
+    _reduce_row(P, X, Y, p_l, m0)
+    for i in range(1, n):
+        Xp, X = X, Y
+        Y = [P.tmp() for _ in range(n)]
+        P.op("add.cc", X[0], X[0], Xp[1])
+        for k in range(n):
+            src = Xp[k + 2] if k + 2 < n else 0
+            P.op("addc.cc" if k < n - 1 else "addc", Y[k], src, 0)
+        _reduce_row(P, X, Y, p_l, m0)
+    T = [P.tmp() for _ in range(n)]
+    P.op("add.cc", T[0], X[1], Y[0])
+    for k in range(1, n - 1):
+        P.op("addc.cc", T[k], X[k + 1], Y[k])
+    P.op("addc", T[n - 1], Y[n - 1], 0)
+    return T
+
+
+def prog_sqr(n, p):
+    """Montgomery square a*a/R mod p with the off-diagonal products computed once:
+    n(n-1)/2 + n wide MACs for a^2 (instead of n^2) plus the n^2 + n of the reduction rows; the doubling and
+    the three 2n-limb carry chains run on the ALU pipe, which has slack next to the multiplier pipe."""
+    assert n % 2 == 0
+    A = ["a%d" % i for i in range(n)]
+    m0 = (-pow(p, -1, 1 << 32)) & MASK
+    P = Prog("sqr", A + _opaque_inputs(p, n), n)
+    p_l = limbs(p, n)
+    # two accumulators so that the (lo, hi) pairs of one carry chain never overlap: EV holds pairs that start at
+    # even limb positions, OD pairs that start at odd positions
+    EV = [P.tmp() for _ in range(2 * n)]
+    OD = [P.tmp() for _ in range(2 * n)]
+    for k in range(2 * n):
+        P.op("mov", EV[k], 0)
+        P.op("mov", OD[k], 0)
+    for i in range(n - 1):
+        for first_j in (i + 1, i + 2):
+            js = list(range(first_j, n, 2))
+            if not js:
+                continue
+            acc = OD if (i + first_j) % 2 else EV
+            for idx, j in enumerate(js):
+                pos = i + j
+                P.op("mad.lo.cc" if idx == 0 else "madc.lo.cc", acc[pos], A[i], A[j], acc[pos])
+                P.op("madc.hi.cc", acc[pos + 1], A[i], A[j], acc[pos + 1])
+            top = i + js[-1] + 1
+            # absorb the chain's carry (the limbs above `top` hold at most earlier carries)
+            # (top <= 2n - 2: the product a_{n-2} a_{n-1} ends at limb 2n - 2)
+            if top + 2 < 2 * n:
+                P.op("addc.cc", acc[top + 1], acc[top + 1], 0)
+                P.op("addc", acc[top + 2], acc[top + 2], 0)
+            else:
+                P.op("addc", acc[top + 1], acc[top + 1], 0)
+    # S = EV + OD ; T = 2 S + diag
+    S = [P.tmp() for _ in range(2 * n)]
+    P.op("add.cc", S[0], EV[0], OD[0])
+    for k in range(1, 2 * n - 1):
+        P.op("addc.cc", S[k], EV[k], OD[k])
+    P.op("addc", S[2 * n - 1], EV[2 * n - 1], OD[2 * n - 1])
+    S2 = [P.tmp() for _ in range(2 * n)]
+    P.op("add.cc", S2[0], S[0], S[0])
+    for k in range(1, 2 * n - 1):
+        P.op("addc.cc", S2[k], S[k], S[k])
+    P.op("addc", S2[2 * n - 1], S[2 * n - 1], S[2 * n - 1])
+    D = [P.tmp() for _ in range(2 * n)]
+    for i in range(n):
+        P.op("mul.lo", D[2 * i], A[i], A[i])
+        P.op("mul.hi", D[2 * i + 1], A[i], A[i])
+    T = [P.tmp() for _ in range(2 * n)]
+    P.op("add.cc", T[0], S2[0], D[0])
+    for k in range(1, 2 * n - 1):
+        P.op("addc.cc", T[k], S2[k], D[k])
+    P.op("addc", T[2 * n - 1], S2[2 * n - 1], D[2 * n - 1])
+    # Montgomery-reduce the low half, then add the high half:  (T_lo + q p) / R + T_hi  <  2p
+    X = [P.tmp() for _ in range(n)]
+    Y = [P.tmp() for _ in range(n)]
+    for k in range(n):
+        P.op("mov", X[k], T[k])
+        P.op("mov", Y[k], 0)
+    Tr = _mont_rows(P, X, Y, p_l, m0, n)
+    U = [P.tmp() for _ in range(n)]
+    P.op("add.cc", U[0], Tr[0], T[n])
+    for k in range(1, n - 1):
+        P.op("addc.cc", U[k], Tr[k], T[n + k])
+    P.op("addc", U[n - 1], Tr[n - 1], T[2 * n - 1])
+    _cond_sub_p(P, U, p_l, P.outputs)
+    return P
+
+
 def prog_from_mont(n, p):
     """a / R mod p  (Montgomery reduction of a single-width value; n^2+n wide MACs)."""
     A = ["a%d" % i for i in range(n)]
     m0 = (-pow(p, -1, 1 << 32)) & MASK
-    P = Prog("from_mont", A + (["m0r"] if m0 == MASK else []), n)
+    P = Prog("from_mont", A + _opaque_inputs(p, n), n)
     p_l = limbs(p, n)
     X = [P.tmp() for _ in range(n)]
     Y = [P.tmp() for _ in range(n)]
@@ -292,7 +414,10 @@ def programs(n, p):
         "add": prog_add(n, p),
         "sub": prog_sub(n, p),
         "mul": prog_mul(n, p),
-        "sqr": prog_mul(n, p, b_is_a=True),
+        # the dedicated squaring (prog_sqr) saves 22% of the wide MACs of a square but its three 2n-limb carry
+        # chains lengthen the dependent instruction stream: measured -4% on the bucket-accumulation kernel, which
+        # runs at ~82% of the IMAD.WIDE pipe and is otherwise latency-limited.  Opt-in with B200_GEN_SQR=1.
+        "sqr": prog_sqr(n, p) if os.environ.get("B200_GEN_SQR") else prog_mul(n, p, b_is_a=True),
         "from_mont": prog_from_mont(n, p),
     }
 
@@ -313,6 +438,8 @@ def emit_fn(prog, fname, n, arity):
         ins += ", " + ", ".join('"r"(b[%d])' % i for i in range(n))
     if "m0r" in prog.inputs:
         ins += ', "r"(k_m0_opaque[0])'
+    if "zr" in prog.inputs:
+        ins += ', "r"(k_m0_opaque[1])'
     out.append("      : %s" % outs)
     out.append("      : %s);" % ins)
     out.append("    " + " ".join("r[%d] = o%d;" % (i, i) for i in range(n)))
@@ -331,7 +458,7 @@ def emit_field(name, p, n):
     hdr.append("#ifndef B200_M0_OPAQUE_DEFINED")
     hdr.append("#define B200_M0_OPAQUE_DEFINED")
     hdr.append("// read through the constant bank so ptxas cannot see that M0 == 2^32-1 (see gen_field.py)")
-    hdr.append("static __device__ __constant__ uint32_t k_m0_opaque[1] = {0xffffffffu};")
+    hdr.append("static __device__ __constant__ uint32_t k_m0_opaque[2] = {0xffffffffu, 0u};")
     hdr.append("#endif")
     hdr.append("struct %s {" % name)
     hdr.append("  static constexpr int N = %d;" % n)
