@@ -78,6 +78,7 @@ _PROTOS = {
     "b200_kzg_srs_register": (_i, [_vp, _u32, C.POINTER(_u64)]),
     "b200_kzg_srs_release": (_i, [_u64]),
     "b200_blob_commit": (_i, [_u64, _vp, _vp, _i]),
+    "b200_blob_proof": (_i, [_u64, _vp, _vp, _vp, _vp, _i]),
     "b200_init": (_i, [_u32]),
     "b200_device_count": (_i, []),
     "b200_last_error": (C.c_char_p, []),

@@ -198,6 +198,12 @@ struct CurveBackend {
   virtual void g1_decompress(const void* d_bytes, void* d_affine, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;
   virtual void g1_compress(const void* d_affine, void* d_bytes, uint32_t n, cudaStream_t s) = 0;
   virtual void blob_to_scalars(const void* d_blob, void* d_scalars, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;
+  // KZG opening (EIP-4844 compute_kzg_proof_impl): roots = w^brp(i) table; kzg_open turns the blob's scalars p and
+  // the point z (32 big-endian bytes on the device) into the quotient evaluations q and y = p(z) (32 bytes).
+  // scratch: (n + 2 * ceil(n / 128) + 2) fr elements + 4 bytes
+  virtual void kzg_roots(void* d_roots, uint32_t n, cudaStream_t s) = 0;
+  virtual void kzg_open(const void* d_p, const void* d_roots, const void* d_z_be, uint32_t n, void* d_q, void* d_y_bytes,
+                        void* d_scratch, uint32_t* d_err, cudaStream_t s) = 0;
   // --- point helpers
   virtual void to_affine(int group, const void* d_xyzz, void* d_affine, uint32_t count, cudaStream_t s) = 0;
   // affine(sum of count XYZZ points): combine of range-split MSM partials

@@ -430,6 +430,21 @@ int b200_blob_commit(uint64_t h, const uint8_t* blob, uint8_t commitment_out[48]
   });
 }
 
+int b200_blob_proof(uint64_t h, const uint8_t* blob, const uint8_t point_be[32], uint8_t proof_out[48],
+                    uint8_t claim_out[32], int device) {
+  return guarded([&] {
+    if (!blob || !point_be || !proof_out || !claim_out) throw std::runtime_error("null argument");
+    std::shared_ptr<KzgSrsDev> srs;
+    {
+      std::lock_guard<std::mutex> lk(g_hmu);
+      auto it = g_srs.find(h);
+      if (it == g_srs.end()) throw std::runtime_error("unknown SRS handle");
+      srs = it->second;
+    }
+    srs->blob_proof(blob, point_be, proof_out, claim_out, device);
+  });
+}
+
 // ---------------------------------------------------------------------------------- setup / instrumentation
 int b200_fixed_base_dev(int curve_id, int group, const void* d_base_affine, const void* d_scalars, uint64_t n,
                         void* d_out_affine, void* stream) {

@@ -580,6 +580,42 @@ struct CurveImpl : CurveBackend {
     }
   }
 
+  void kzg_roots(void* d_roots, uint32_t n, cudaStream_t s) override {
+    if constexpr (Cfg::ID == 3) {
+      int logn = 0;
+      while ((1u << logn) < n) logn++;
+      k_kzg_roots<Fr><<<(n + 127) / 128, 128, 0, s>>>((FrEl*)d_roots, n, logn);
+      B200_CUDA(cudaGetLastError());
+    } else {
+      throw std::runtime_error("kzg_roots: only BLS12-381 is supported");
+    }
+  }
+  void kzg_open(const void* d_p, const void* d_roots, const void* d_z_be, uint32_t n, void* d_q, void* d_y_bytes,
+                void* d_scratch, uint32_t* d_err, cudaStream_t s) override {
+    if constexpr (Cfg::ID == 3) {
+      int logn = 0;
+      while ((1u << logn) < n) logn++;
+      const uint32_t nblocks = (n + kKzgThreads - 1) / kKzgThreads;
+      FrEl* inv = (FrEl*)d_scratch;
+      FrEl* partial = inv + n;
+      FrEl* partial2 = partial + nblocks;
+      FrEl* z = partial2 + nblocks;
+      FrEl* y = z + 1;
+      uint32_t* hit = (uint32_t*)(y + 1);
+      const FrEl* p = (const FrEl*)d_p;
+      const FrEl* roots = (const FrEl*)d_roots;
+      k_kzg_load_point<Fr><<<1, 1, 0, s>>>((const uint8_t*)d_z_be, z, hit, d_err);
+      k_kzg_open_terms<Fr><<<nblocks, kKzgThreads, 0, s>>>(p, roots, z, inv, partial, hit, n);
+      k_kzg_open_y<Fr><<<1, 32, 0, s>>>(partial, nblocks, p, z, hit, n, logn, y, (uint8_t*)d_y_bytes);
+      k_kzg_open_quotient<Fr><<<nblocks, kKzgThreads, 0, s>>>(p, roots, inv, y, (FrEl*)d_q, partial2, n);
+      k_kzg_open_fix<Fr><<<1, 32, 0, s>>>(partial2, nblocks, z, hit, (FrEl*)d_q);
+      prof_count_launches(5);
+      B200_CUDA(cudaGetLastError());
+    } else {
+      throw std::runtime_error("kzg_open: only BLS12-381 is supported");
+    }
+  }
+
   void scale_vec(void* d_x, const void* d_c, uint64_t n, cudaStream_t s) override {
     if (!n) return;
     k_scale_vec<Fr><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((FrEl*)d_x, (const FrEl*)d_c, n);

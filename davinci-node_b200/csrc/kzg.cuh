@@ -147,4 +147,167 @@ __global__ void k_blob_to_scalars(const uint8_t* __restrict__ blob, typename Fr:
   out[i] = v;
 }
 
+// ------------------------------------------------------------------------------------ opening proofs
+// EIP-4844 compute_kzg_proof_impl on the device: the blob is p's evaluations over the n-th roots of unity in
+// bit-reversed order; proof = MSM(q, Lagrange SRS) with q_i = (p_i - y) / (w_i - z), y = p(z) by the
+// barycentric formula.  Replaces go-ethereum `kzg4844.ComputeProof` / `ComputeBlobProof`
+// (/root/reference/types/blobs.go:107-134).
+constexpr int kKzgThreads = 128;
+
+// roots[i] = w^brp(i), w = (2^32-th root of unity of BLS12-381 fr, crypto/blobs/barycentric.go:52)^(2^(32-logn))
+template <class Fr>
+__global__ void k_kzg_roots(typename Fr::El* __restrict__ roots, uint32_t n, int logn) {
+  using El = typename Fr::El;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr uint32_t g32[8] = {0x439f0d2bu, 0x3829971fu, 0x8c2280b9u, 0xb6368350u,
+                               0x22c813b4u, 0xd09b6819u, 0xdfe81f20u, 0x16a2a19eu};
+  El w, acc;
+#pragma unroll
+  for (int k = 0; k < 8; k++) w.v[k] = g32[k];
+  Fr::to_mont(w, w);
+  for (int k = 0; k < 32 - logn; k++) Fr::sqr(w, w);
+  uint32_t e = logn ? (__brev(i) >> (32 - logn)) : 0;
+  Fr::set_one(acc);
+  while (e) {
+    if (e & 1) Fr::mul(acc, acc, w);
+    e >>= 1;
+    if (e) Fr::sqr(w, w);
+  }
+  roots[i] = acc;
+}
+
+// block-wide sum of Fr elements; result valid in thread 0
+template <class Fr>
+__device__ __forceinline__ void kzg_block_sum(typename Fr::El& v, typename Fr::El* sm) {
+  sm[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = kKzgThreads / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      Fr::add(v, v, sm[threadIdx.x + s]);
+      sm[threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// z: 32 big-endian bytes -> Montgomery; err bit 3 when z >= r
+template <class Fr>
+__global__ void k_kzg_load_point(const uint8_t* __restrict__ z_be, typename Fr::El* __restrict__ z_out, uint32_t* hit,
+                                 uint32_t* err) {
+  using P = typename Fr::Params;
+  typename Fr::El v;
+  uint8_t buf[32];
+  for (int k = 0; k < 32; k++) buf[k] = z_be[k];
+  be_bytes_to_limbs<Fr::N>(v.v, buf);
+  bool lt = false;
+  for (int k = Fr::N - 1; k >= 0; k--) {
+    if (v.v[k] < P::modulus(k)) {
+      lt = true;
+      break;
+    }
+    if (v.v[k] > P::modulus(k)) break;
+  }
+  if (!lt) atomicOr(err, 8u);
+  Fr::to_mont(v, v);
+  *z_out = v;
+  *hit = 0xffffffffu;
+}
+
+// inv[i] = 1/(z - w_i) (0 when z == w_i, whose index goes to *hit); partial[block] = sum p_i w_i inv_i
+template <class Fr>
+__global__ void __launch_bounds__(kKzgThreads)
+k_kzg_open_terms(const typename Fr::El* __restrict__ p, const typename Fr::El* __restrict__ roots,
+                 const typename Fr::El* __restrict__ z, typename Fr::El* __restrict__ inv,
+                 typename Fr::El* __restrict__ partial, uint32_t* __restrict__ hit, uint32_t n) {
+  using El = typename Fr::El;
+  __shared__ El sm[kKzgThreads];
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  El term;
+  Fr::set_zero(term);
+  if (i < n) {
+    El d, w = roots[i], iv;
+    Fr::sub(d, *z, w);
+    if (Fr::is_zero(d)) atomicMin(hit, i);
+    Fr::inv(iv, d);
+    inv[i] = iv;
+    Fr::mul(term, p[i], w);
+    Fr::mul(term, term, iv);
+  }
+  kzg_block_sum<Fr>(term, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = term;
+}
+
+// y = p(z): p[hit] inside the domain, else (z^n - 1)/n * sum of the partials.  Also as 32 big-endian bytes.
+template <class Fr>
+__global__ void k_kzg_open_y(const typename Fr::El* __restrict__ partial, uint32_t nblocks,
+                             const typename Fr::El* __restrict__ p, const typename Fr::El* __restrict__ z,
+                             const uint32_t* __restrict__ hit, uint32_t n, int logn, typename Fr::El* __restrict__ y_out,
+                             uint8_t* __restrict__ y_bytes) {
+  using El = typename Fr::El;
+  if (threadIdx.x || blockIdx.x) return;
+  El y;
+  if (*hit != 0xffffffffu) {
+    y = p[*hit];
+  } else {
+    El s, zn = *z, one, nn, ninv;
+    Fr::set_zero(s);
+    for (uint32_t k = 0; k < nblocks; k++) Fr::add(s, s, partial[k]);
+    for (int k = 0; k < logn; k++) Fr::sqr(zn, zn);
+    Fr::set_one(one);
+    Fr::sub(zn, zn, one);
+    nn = one;
+    for (int k = 0; k < logn; k++) Fr::dbl(nn, nn);
+    Fr::inv(ninv, nn);
+    Fr::mul(y, s, zn);
+    Fr::mul(y, y, ninv);
+  }
+  *y_out = y;
+  El yc;
+  Fr::from_mont(yc, y);
+  uint8_t buf[32];
+  limbs_to_be_bytes<Fr::N>(buf, yc.v);
+  for (int k = 0; k < 32; k++) y_bytes[k] = buf[k];
+}
+
+// q_i = (p_i - y) / (w_i - z) = -(p_i - y) inv_i ; partial2[block] = sum (p_i - y) w_i inv_i
+template <class Fr>
+__global__ void __launch_bounds__(kKzgThreads)
+k_kzg_open_quotient(const typename Fr::El* __restrict__ p, const typename Fr::El* __restrict__ roots,
+                    const typename Fr::El* __restrict__ inv, const typename Fr::El* __restrict__ y,
+                    typename Fr::El* __restrict__ q, typename Fr::El* __restrict__ partial2, uint32_t n) {
+  using El = typename Fr::El;
+  __shared__ El sm[kKzgThreads];
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  El term;
+  Fr::set_zero(term);
+  if (i < n) {
+    El t, u;
+    Fr::sub(t, p[i], *y);
+    Fr::mul(u, t, inv[i]);
+    Fr::mul(term, u, roots[i]);
+    Fr::neg(u, u);
+    q[i] = u;
+  }
+  kzg_block_sum<Fr>(term, sm);
+  if (threadIdx.x == 0) partial2[blockIdx.x] = term;
+}
+
+// z inside the domain (z = w_hit): q_hit = (1/z) sum_{i != hit} (p_i - y) w_i / (z - w_i)
+// (EIP-4844 compute_quotient_eval_within_domain; the i = hit term of the partial sums is zero because inv_hit = 0)
+template <class Fr>
+__global__ void k_kzg_open_fix(const typename Fr::El* __restrict__ partial2, uint32_t nblocks,
+                               const typename Fr::El* __restrict__ z, const uint32_t* __restrict__ hit,
+                               typename Fr::El* __restrict__ q) {
+  using El = typename Fr::El;
+  if (threadIdx.x || blockIdx.x) return;
+  if (*hit == 0xffffffffu) return;
+  El s, zi;
+  Fr::set_zero(s);
+  for (uint32_t k = 0; k < nblocks; k++) Fr::add(s, s, partial2[k]);
+  Fr::inv(zi, *z);
+  Fr::mul(s, s, zi);
+  q[*hit] = s;
+}
+
 }  // namespace b200

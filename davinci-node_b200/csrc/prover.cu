@@ -427,6 +427,11 @@ std::unique_ptr<KzgSrsDev> KzgSrsDev::create(const uint8_t* g1_lagrange_compress
     in->blob.get((size_t)npoints * 32);
     in->scalars.get((size_t)npoints * cb->fr_bytes());
     in->out.get(cb->xyzz_bytes(1) + g1b + 64);
+    const size_t frb = cb->fr_bytes();
+    cb->kzg_roots(in->roots.get((size_t)npoints * frb), npoints, in->st);
+    in->quot.get((size_t)npoints * frb);
+    in->scratch.get(((size_t)npoints + 2 * ((npoints + 127) / 128) + 2) * frb + 16);
+    in->zbuf.get(64);
     uint32_t herr = 0;
     B200_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, in->st));
     B200_CUDA(cudaStreamSynchronize(in->st));
@@ -441,15 +446,42 @@ KzgSrsDev::Inst::~Inst() {
   if (st) cudaStreamDestroy(st);
 }
 
-void KzgSrsDev::blob_commit(const uint8_t* blob, uint8_t* commitment48, int device) {
-  Inst* I = nullptr;
+KzgSrsDev::Inst& KzgSrsDev::pick(int device) {
   if (device >= 0) {
     for (auto& in : inst)
-      if (in->device == device) I = in.get();
-    if (!I) throw std::runtime_error("SRS is not resident on device " + std::to_string(device));
-  } else {
-    I = inst[rr.fetch_add(1) % inst.size()].get();
+      if (in->device == device) return *in;
+    throw std::runtime_error("SRS is not resident on device " + std::to_string(device));
   }
+  return *inst[rr.fetch_add(1) % inst.size()];
+}
+
+void KzgSrsDev::blob_proof(const uint8_t* blob, const uint8_t* z32, uint8_t* proof48, uint8_t* y32, int device) {
+  Inst* I = &pick(device);
+  std::lock_guard<std::mutex> lk(I->mu);
+  DeviceScope ds(I->device);
+  const size_t g1b = cb->affine_bytes(1), x1 = cb->xyzz_bytes(1);
+  uint32_t* err = (uint32_t*)I->err.p;
+  uint8_t* zb = (uint8_t*)I->zbuf.p;   // [z (32) | y (32)]
+  B200_CUDA(cudaMemsetAsync(err, 0, 4, I->st));
+  B200_CUDA(cudaMemcpyAsync(I->blob.p, blob, (size_t)npoints * 32, cudaMemcpyHostToDevice, I->st));
+  B200_CUDA(cudaMemcpyAsync(zb, z32, 32, cudaMemcpyHostToDevice, I->st));
+  cb->blob_to_scalars(I->blob.p, I->scalars.p, npoints, err, I->st);
+  cb->kzg_open(I->scalars.p, I->roots.p, zb, npoints, I->quot.p, zb + 32, I->scratch.p, err, I->st);
+  uint8_t* o = (uint8_t*)I->out.p;
+  cb->msm(1, nullptr, I->quot.p, npoints, o, I->ws, I->st, 0, nullptr, (const uint32_t*)I->brp.p, &I->tables);
+  cb->to_affine(1, o, o + x1, 1, I->st);
+  cb->g1_compress(o + x1, o + x1 + g1b, 1, I->st);
+  uint32_t herr = 0;
+  B200_CUDA(cudaMemcpyAsync(proof48, o + x1 + g1b, 48, cudaMemcpyDeviceToHost, I->st));
+  B200_CUDA(cudaMemcpyAsync(y32, zb + 32, 32, cudaMemcpyDeviceToHost, I->st));
+  B200_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, I->st));
+  B200_CUDA(cudaStreamSynchronize(I->st));
+  if (herr & 8u) throw std::runtime_error("evaluation point is not a canonical field element (>= BLS12-381 r)");
+  if (herr) throw std::runtime_error("blob contains a non-canonical field element (>= BLS12-381 r)");
+}
+
+void KzgSrsDev::blob_commit(const uint8_t* blob, uint8_t* commitment48, int device) {
+  Inst* I = &pick(device);
   std::lock_guard<std::mutex> lk(I->mu);
   DeviceScope ds(I->device);
   const size_t g1b = cb->affine_bytes(1), x1 = cb->xyzz_bytes(1);

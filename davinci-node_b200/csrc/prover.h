@@ -65,7 +65,7 @@ struct KzgSrsDev {
     std::mutex mu;
     cudaStream_t st = nullptr;
     MsmBases tables;
-    DevBuf brp, blob, scalars, out, err;
+    DevBuf brp, blob, scalars, out, err, roots, quot, scratch, zbuf;
     MsmWorkspace ws;
     ~Inst();
   };
@@ -76,6 +76,9 @@ struct KzgSrsDev {
   static std::unique_ptr<KzgSrsDev> create(const uint8_t* g1_lagrange_compressed, uint32_t npoints,
                                            const std::vector<int>& devices);
   void blob_commit(const uint8_t* blob, uint8_t* commitment48, int device);
+  // KZG opening at z (32 big-endian bytes): 48-byte proof and the claimed value y = p(z) (32 big-endian bytes)
+  void blob_proof(const uint8_t* blob, const uint8_t* z32, uint8_t* proof48, uint8_t* y32, int device);
+  Inst& pick(int device);
 };
 
 }  // namespace b200

@@ -1,5 +1,6 @@
 """Mirror of the reference's blob-commitment boundary: `types.Blob.ComputeCommitment`
-(/root/reference/types/blobs.go:90-96 -> gethkzg.BlobToCommitment), on the GPU.
+(/root/reference/types/blobs.go:90-96 -> gethkzg.BlobToCommitment), `ComputeProof` and `ComputeBlobProof`
+(types/blobs.go:107-134), on the GPU.
 
 The EIP-4844 SRS (4096 G1 Lagrange points, 48-byte compressed, the order of
 /root/reference/config/kzg_trusted_setup.txt) is registered once, decompressed on the device and
@@ -12,6 +13,7 @@ import numpy as np
 from . import capi
 
 BLOB_BYTES = 4096 * 32
+BLS_MODULUS = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 _lock = threading.Lock()
 _srs_handle = None
 
@@ -56,3 +58,31 @@ class Blob:
         except capi.B200Error as e:
             raise BlobError(str(e)) from e
         return bytes(out)
+
+    def ComputeProof(self, point: int, device=-1):
+        """types/blobs.go:123: KZG proof at `point` for the blob polynomial -> (48-byte proof, claim y as int).
+        Raises BlobError when |point| does not fit 32 bytes or is not a canonical field element."""
+        if _srs_handle is None:
+            raise BlobError("trusted setup not loaded (call load_trusted_setup first)")
+        if point < 0 or point.bit_length() > 256:
+            raise BlobError("point does not fit in 32 bytes")
+        blob = np.frombuffer(self.data, dtype=np.uint8)
+        z = np.frombuffer(point.to_bytes(32, "big"), dtype=np.uint8)
+        proof = np.zeros(48, dtype=np.uint8)
+        claim = np.zeros(32, dtype=np.uint8)
+        try:
+            capi.check(capi.lib.b200_blob_proof(_srs_handle, blob.ctypes.data, z.ctypes.data, proof.ctypes.data,
+                                                claim.ctypes.data, device))
+        except capi.B200Error as e:
+            raise BlobError(str(e)) from e
+        return bytes(proof), int.from_bytes(bytes(claim), "big")
+
+    def ComputeBlobProof(self, commitment: bytes, device=-1) -> bytes:
+        """types/blobs.go:111: the proof that verifies the blob against `commitment` (opening at the
+        Fiat-Shamir challenge; the SHA-256 transcript hash is host work, as in geth)."""
+        import hashlib
+        if len(commitment) != 48:
+            raise BlobError("commitment must be 48 bytes")
+        data = b"FSBLOBVERIFY_V1_" + (BLOB_BYTES // 32).to_bytes(16, "big") + self.data + bytes(commitment)
+        z = int.from_bytes(hashlib.sha256(data).digest(), "big") % BLS_MODULUS
+        return self.ComputeProof(z, device)[0]

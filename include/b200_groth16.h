@@ -172,6 +172,14 @@ B200_API int b200_kzg_srs_register(const uint8_t* g1_lagrange, uint32_t npoints,
 B200_API int b200_kzg_srs_release(uint64_t handle);
 B200_API int b200_blob_commit(uint64_t srs, const uint8_t* blob /* npoints*32 bytes */, uint8_t commitment_out[48],
                               int device);
+/* KZG opening proof of the blob polynomial at `point` (32 big-endian bytes, canonical): proof_out = 48-byte
+ * compressed commitment to (p(X) - p(z)) / (X - z), claim_out = y = p(z) as 32 big-endian bytes.  Replaces
+ * gethkzg.ComputeProof (types/blobs.go:123-134); with point = the Fiat-Shamir challenge
+ * sha256("FSBLOBVERIFY_V1_" || u128(4096) || blob || commitment) mod r, computed by the host shim, it is
+ * gethkzg.ComputeBlobProof (types/blobs.go:111-117).  Points inside the evaluation domain are handled as in
+ * EIP-4844 compute_quotient_eval_within_domain. */
+B200_API int b200_blob_proof(uint64_t srs, const uint8_t* blob, const uint8_t point_be[32], uint8_t proof_out[48],
+                             uint8_t claim_out[32], int device);
 
 /* ---- setup building block / instrumentation -----------------------------------------------------
  * out[i] = [k_i] base as affine points: the fixed-base batch scalar multiplication groth16.Setup is

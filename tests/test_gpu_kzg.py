@@ -64,3 +64,54 @@ def test_non_canonical_blob_is_rejected(kz):
         kz.Blob(bytes(blob)).ComputeCommitment()
     with pytest.raises(kz.BlobError):
         kz.Blob(b"\x00" * 100)
+
+
+def _lag():
+    raw = open(os.path.join(GOLD, "kzg_g1_lagrange.bin"), "rb").read()
+    return [OK.g1_decompress(raw[i:i + 48]) for i in range(0, len(raw), 48)]
+
+
+def test_opening_proof_vs_oracle(kz):
+    """Blob.ComputeProof (types/blobs.go:123): proof and claim equal the oracle's for a point outside the
+    domain, a point inside it (EIP-4844 compute_quotient_eval_within_domain) and z = 0."""
+    lag = _lag()
+    rnd = random.Random(21)
+    r = OP.BLS12_381.r
+    cells = [rnd.randrange(OP.BN254.r) for _ in range(2193)] + [0] * (4096 - 2193)
+    blob = b"".join(v.to_bytes(32, "big") for v in cells)
+    roots = OK.roots_of_unity_brp(4096)
+    for z in (rnd.randrange(r), roots[1234], 0):
+        proof, y = kz.Blob(blob).ComputeProof(z)
+        want_proof, want_y = OK.compute_proof(blob, z, lag)
+        assert y == want_y, hex(z)
+        assert proof == want_proof, hex(z)
+
+
+def test_blob_proof_vs_oracle_and_linearity(kz):
+    """ComputeBlobProof (types/blobs.go:111) against the oracle; and, as a size-independent property, the opening
+    proof is linear in the blob: proof(p1 + p2, z) = proof(p1, z) + proof(p2, z), y likewise."""
+    from oracle import curve as OC
+    lag = _lag()
+    cx = OC.ctx("bls12_381")
+    rnd = random.Random(22)
+    r = OP.BLS12_381.r
+    c1 = [rnd.randrange(r) for _ in range(4096)]
+    c2 = [rnd.randrange(r) for _ in range(4096)]
+    enc = lambda cs: b"".join(v.to_bytes(32, "big") for v in cs)
+    b1, b2, b12 = enc(c1), enc(c2), enc([(a + b) % r for a, b in zip(c1, c2)])
+    com = kz.Blob(b1).ComputeCommitment()
+    assert kz.Blob(b1).ComputeBlobProof(com) == OK.compute_blob_proof(b1, com, lag)
+    z = rnd.randrange(r)
+    (p1, y1), (p2, y2), (p12, y12) = (kz.Blob(b).ComputeProof(z) for b in (b1, b2, b12))
+    assert y12 == (y1 + y2) % r
+    assert OK.g1_decompress(p12) == cx.G1.add(OK.g1_decompress(p1), OK.g1_decompress(p2))
+
+
+def test_opening_point_must_be_canonical(kz):
+    blob = bytes(4096 * 32)
+    with pytest.raises(kz.BlobError):
+        kz.Blob(blob).ComputeProof(OP.BLS12_381.r)
+    with pytest.raises(kz.BlobError):
+        kz.Blob(blob).ComputeProof(1 << 256)
+    proof, y = kz.Blob(blob).ComputeProof(5)           # zero polynomial: quotient 0 -> point at infinity, y = 0
+    assert y == 0 and proof == bytes([0xC0]) + bytes(47)
