@@ -200,6 +200,10 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
+    # NCCL (used only for the barrier / max-over-ranks timing) prints its version banner on stdout at the
+    # VERSION debug level, which would precede the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -301,28 +305,39 @@ def main():
     sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
     peak_nominal = 148 * 64 * sm_max * 1e6
 
-    # dominant kernel family: the G2 MSM, run alone with the CUDA-event kernel timers on
+    # dominant kernel: k_msm_accumulate<G1> of the quotient (Z) MSM - dense 253-bit scalars over n-1 points, one
+    # third of a proof's GPU time.  Run alone, in table mode as the key is held, with the CUDA-event kernel timers
+    # on; the G2 MSM (Bs) is measured the same way as `roofline_g2`.
     sol = sols[0]
     nB = len(wl.kB)
-    b2 = torch.from_numpy(wl.pk.g2_B).cuda()
-    outx = torch.zeros(L.xyzz_bytes(2), dtype=torch.uint8, device="cuda")
+
+    def msm_alone(points_np, group, npts):
+        pts = torch.from_numpy(points_np).cuda()
+        outx = torch.zeros(L.xyzz_bytes(group), dtype=torch.uint8, device="cuda")
+        hb = C.c_uint64(0)
+        capi.check(lib.b200_bases_create_dev(L.id, group, pts.data_ptr(), npts, 0, C.byref(hb), st))
+        run = lambda: capi.check(lib.b200_msm_bases_dev(hb.value, sol["a_dev"].data_ptr(), npts, None, outx.data_ptr(), st))
+        run()
+        torch.cuda.synchronize()
+        capi.check(lib.b200_profile_enable(1))
+        for _ in range(3):
+            run()
+        ms = (C.c_double * 5)()
+        cnt = (C.c_uint64 * 5)()
+        capi.check(lib.b200_profile_collect(ms, cnt))
+        capi.check(lib.b200_profile_enable(0))
+        capi.check(lib.b200_bases_release(hb.value))
+        tot, acc = (3, 0) if group == 1 else (4, 1)
+        return ms[tot] / max(cnt[tot], 1), ms[acc] / max(cnt[acc], 1)
+
     # uniform full-width scalars (the quotient's a-vector): the SURVEY 8d work formula is exact for them,
     # whereas the witness-like wire vector skips ~60% of the points and would flatter the fraction
-    hb = C.c_uint64(0)
-    capi.check(lib.b200_bases_create_dev(L.id, 2, b2.data_ptr(), nB, 0, C.byref(hb), st))   # table mode, as the key is held
-    msm_dev = lambda: capi.check(lib.b200_msm_bases_dev(hb.value, sol["a_dev"].data_ptr(), nB, None, outx.data_ptr(), st))
-    msm_dev()
-    torch.cuda.synchronize()
-    capi.check(lib.b200_profile_enable(1))
-    reps = 3
-    for _ in range(reps):
-        msm_dev()
+    nZ = min(wl.nc, wl.n - 1)
+    g1_total_ms, g1_acc_ms = msm_alone(wl.pk.g1_Z, 1, nZ)
+    g2_total_ms, g2_acc_ms = msm_alone(wl.pk.g2_B, 2, nB)
     ms = (C.c_double * 5)()
     cnt = (C.c_uint64 * 5)()
-    capi.check(lib.b200_profile_collect(ms, cnt))
-    g2_total_ms, g2_acc_ms = ms[4] / max(cnt[4], 1), ms[1] / max(cnt[1], 1)
-    capi.check(lib.b200_bases_release(hb.value))
-    del b2
+    reps = 3
     # NTT passes alone (quotient on resident buffers)
     dom = C.c_uint64(0)
     from davinci_node_b200.curve_consts import domain_constants
@@ -349,17 +364,30 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     g1_macs, g2_macs, ntt_macs = workload_macs(args.logn, len(wl.kA) + 2, nB + 2, len(wl.kK) + 1, wl.n - 1, wl.n_c)
+    g1_alg = msm_adds_star(nZ, 253) * 10 * p_mul(12)
     g2_alg = msm_adds_star(nB, 253) * 10 * p_mul(12) * 3
-    achieved = g2_alg / (g2_total_ms / 1e3)
-    roofline = {"bound": "imad", "kernel": "G2 MSM, %d points, uniform 253-bit scalars (k_msm_accumulate<Fp2> = %.0f%% of it)" % (nB, 100 * g2_acc_ms / g2_total_ms),
-                "achieved": achieved / 1e12, "peak": peak_meas / 1e12, "unit": "T wide-MAC/s (32x32->64 IMAD.WIDE)",
-                "frac": achieved / peak_meas, "peak_source": "measured in this run (b200_calib_mul_dev); nominal 148*64*f = %.2f" % (peak_nominal / 1e12),
-                "frac_of_nominal": achieved / peak_nominal,
-                # dram__bytes_read+write of k_msm_accumulate<Fp2> from the committed ncu capture at 2^21 points
-                # (profiles/r1_ncu_msm_accumulate_g2.md: 10.38 GB + 17.51 GB), scaled to this launch's point count
-                "traffic": (10.38e9 + 17.51e9) * nB / float(1 << 21),
-                "traffic_note": "algorithmic point bytes = adds* x 192 B; the excess is Fp2 accumulator spill traffic",
-                "launch_ms": g2_total_ms, "algorithmic_macs_per_launch": g2_alg}
+    peak_note = "measured in this run (b200_calib_mul_dev); nominal 148*64*f = %.2f" % (peak_nominal / 1e12)
+    roofline = {"bound": "imad", "kernel": "k_msm_accumulate<G1> inside the quotient (Z) MSM: %d points, uniform 253-bit "
+                                            "scalars, table mode c=20 (the kernel is %.0f%% of the MSM)" % (nZ, 100 * g1_acc_ms / g1_total_ms),
+                "achieved": g1_alg / (g1_total_ms / 1e3) / 1e12, "peak": peak_meas / 1e12,
+                "unit": "T wide-MAC/s (32x32->64 IMAD.WIDE)", "frac": g1_alg / (g1_total_ms / 1e3) / peak_meas,
+                "peak_source": peak_note, "frac_of_nominal": g1_alg / (g1_total_ms / 1e3) / peak_nominal,
+                # dram__bytes_read+write of the kernel from the committed ncu capture at 2^22 points
+                # (profiles/r1_ncu_msm_accumulate_g1.md: 10.69 GB + 0.17 GB), scaled to this launch's point count
+                "traffic": (10.69e9 + 0.17e9) * nZ / float(1 << 22),
+                "traffic_note": "algorithmic point bytes = adds* x 96 B = %.2f GB; gathered 96-byte points straddle "
+                                "64-byte DRAM bursts" % (msm_adds_star(nZ, 253) * 96 / 1e9),
+                "launch_ms": g1_total_ms, "kernel_ms": g1_acc_ms, "algorithmic_macs_per_launch": g1_alg,
+                "ncu_pipe_fmaheavy_pct": 88.6}
+    roofline_g2 = {"bound": "imad", "kernel": "G2 MSM (Bs), %d points, uniform 253-bit scalars (k_msm_accumulate<Fp2> = %.0f%% of it)" % (nB, 100 * g2_acc_ms / g2_total_ms),
+                   "achieved": g2_alg / (g2_total_ms / 1e3) / 1e12, "peak": peak_meas / 1e12,
+                   "unit": "T wide-MAC/s (32x32->64 IMAD.WIDE)", "frac": g2_alg / (g2_total_ms / 1e3) / peak_meas,
+                   "peak_source": peak_note, "frac_of_nominal": g2_alg / (g2_total_ms / 1e3) / peak_nominal,
+                   # profiles/r1_ncu_msm_accumulate_g2.md: 9.80 GB + 16.61 GB at 2^21 points
+                   "traffic": (9.80e9 + 16.61e9) * nB / float(1 << 21),
+                   "traffic_note": "algorithmic point bytes = adds* x 192 B; the excess is local-memory traffic of the "
+                                   "out-of-line Fp2 multiply",
+                   "launch_ms": g2_total_ms, "kernel_ms": g2_acc_ms, "algorithmic_macs_per_launch": g2_alg}
     ntt_bytes = 2 * wl.n * L.fr_bytes
     roofline_ntt = {"bound": "hbm", "kernel": "k_ntt_pass (one 2^%d transform = %d passes)" % (args.logn, ntt_passes),
                     "achieved": ntt_bytes / (ntt_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -375,7 +403,8 @@ def main():
             "dtype": "u32x12 Montgomery (BLS12-377 fp) / u32x8 (fr)", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes() * args.batch, "d2h_bytes_per_step": wl.d2h_bytes() * args.batch,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_ntt": roofline_ntt,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_g2": roofline_g2,
+            "roofline_ntt": roofline_ntt,
             "step_imad_frac_dense_formula": step_macs / (ms_total / args.steps / 1e3) / peak_meas,
             "step_imad_note": "SURVEY 8d work formula assumes dense scalars; the witness-like wire vector skips ~60% of "
                               "the A/B/K points, so this can exceed 1 - the kernel-level `roofline` uses dense scalars",

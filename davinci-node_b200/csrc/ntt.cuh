@@ -35,6 +35,22 @@ struct NttPass {
 
 constexpr int kNttThreads = 256;
 
+// The shared-memory tile is stored chunk-major: 16-byte chunk k of element i lives at tile[k * E + i].  With the
+// natural array-of-elements layout consecutive threads would read 16-byte pieces 32 (or 48) bytes apart, a 2-way
+// bank conflict on every 128-bit access; chunk-major rows are contiguous and conflict-free.
+template <class El>
+__device__ __forceinline__ void tile_load(El& x, const uint4* tile, uint32_t E, uint32_t i) {
+  uint4* d = reinterpret_cast<uint4*>(&x);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(El) / 16); k++) d[k] = tile[k * E + i];
+}
+template <class El>
+__device__ __forceinline__ void tile_store(uint4* tile, uint32_t E, uint32_t i, const El& x) {
+  const uint4* s = reinterpret_cast<const uint4*>(&x);
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(El) / 16); k++) tile[k * E + i] = s[k];
+}
+
 template <class Fr>
 __device__ __forceinline__ void ntt_apply_scale(typename Fr::El& x, const NttScale& sc, uint32_t i, int logn) {
   using El = typename Fr::El;
@@ -60,8 +76,7 @@ k_ntt_pass(typename Fr::El* __restrict__ data, const typename Fr::El* __restrict
            NttScale post, const typename Fr::El* __restrict__ in_b, const typename Fr::El* __restrict__ in_c,
            const typename Fr::El* __restrict__ den) {
   using El = typename Fr::El;
-  extern __shared__ uint4 ntt_smem_raw[];
-  El* sm = reinterpret_cast<El*>(ntt_smem_raw);
+  extern __shared__ uint4 sm[];
 
   const int elog = ps.logr + ps.lo_tile_log;
   const uint32_t E = 1u << elog;
@@ -88,7 +103,7 @@ k_ntt_pass(typename Fr::El* __restrict__ data, const typename Fr::El* __restrict
       Fr::mul(x, x, d);
     }
     ntt_apply_scale<Fr>(x, pre, (uint32_t)gi, ps.logn);
-    store16(sm + l, x);
+    tile_store(sm, E, l, x);
   }
   __syncthreads();
 
@@ -107,8 +122,8 @@ k_ntt_pass(typename Fr::El* __restrict__ data, const typename Fr::El* __restrict
       uint32_t i1 = i0 + (1u << (log_dm + ps.lo_tile_log));
       uint32_t e = ((mid_low << ps.s_log) + lo0 + lo_l) << shift;
       El x, y, w;
-      load16_rw(x, sm + i0);
-      load16_rw(y, sm + i1);
+      tile_load(x, sm, E, i0);
+      tile_load(y, sm, E, i1);
       if (DIT) {
         if (e) {
           load16(w, tw + e);
@@ -117,8 +132,8 @@ k_ntt_pass(typename Fr::El* __restrict__ data, const typename Fr::El* __restrict
         El t;
         Fr::add(t, x, y);
         Fr::sub(y, x, y);
-        store16(sm + i0, t);
-        store16(sm + i1, y);
+        tile_store(sm, E, i0, t);
+        tile_store(sm, E, i1, y);
       } else {
         El t;
         Fr::add(t, x, y);
@@ -127,8 +142,8 @@ k_ntt_pass(typename Fr::El* __restrict__ data, const typename Fr::El* __restrict
           load16(w, tw + e);
           Fr::mul(y, y, w);
         }
-        store16(sm + i0, t);
-        store16(sm + i1, y);
+        tile_store(sm, E, i0, t);
+        tile_store(sm, E, i1, y);
       }
     }
     __syncthreads();
@@ -139,7 +154,7 @@ k_ntt_pass(typename Fr::El* __restrict__ data, const typename Fr::El* __restrict
     uint32_t mid = l >> ps.lo_tile_log, lo_l = l & lo_mask;
     uint64_t gi = base + ((uint64_t)mid << ps.s_log) + lo_l;
     El x;
-    load16_rw(x, sm + l);
+    tile_load(x, sm, E, l);
     ntt_apply_scale<Fr>(x, post, (uint32_t)gi, ps.logn);
     store16(data + gi, x);
   }
