@@ -221,10 +221,16 @@ __global__ void k_sum_sets(const uint8_t* __restrict__ partials, uint32_t nparts
 }
 
 // ------------------------------------------------------------------------------------ MSM driver
-// T_j[i] = 2^(c j) P_i for j < nwin (affine, table j at offset j * npts): one thread per point
+// T_j[i] = 2^(c j) P_i for j < nwin (affine, table j at offset j * npts): one thread per point.
+// The XYZZ doubling chain runs through all windows; the nwin - 1 affine normalisations of a point share ONE field
+// inversion (Montgomery's trick over d_j = ZZ_j * ZZZ_j), which is 3x less multiplier work than an inversion per
+// window.  `scratch` holds {ZZ_j, ZZZ_j, prefix product} per (window, point) while the kernel runs; X_j, Y_j wait
+// in their table slot.
 template <class F>
 __global__ void __launch_bounds__(64) k_build_tables(const Affine<F>* __restrict__ base, uint64_t npts, int c, int nwin,
-                                                      Affine<F>* __restrict__ tables) {
+                                                      Affine<F>* __restrict__ tables,
+                                                      typename F::El* __restrict__ scratch) {
+  using El = typename F::El;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npts) return;
   Affine<F> p;
@@ -232,13 +238,49 @@ __global__ void __launch_bounds__(64) k_build_tables(const Affine<F>* __restrict
   store16(tables + i, p);
   XYZZ<F> x;
   EC<F>::from_affine(x, p);
+  El run;
+  F::set_one(run);
   for (int j = 1; j < nwin; j++) {
     for (int k = 0; k < c; k++) EC<F>::dbl(x);
-    Affine<F> o;
-    EC<F>::to_affine(o, x);
+    El* sc = scratch + ((uint64_t)(j - 1) * npts + i) * 3;
+    Affine<F> xy;
+    xy.x = x.x;
+    xy.y = x.y;
+    store16(tables + (uint64_t)j * npts + i, xy);
+    El d;
+    if (EC<F>::is_inf(x)) F::set_one(d);   // infinity (or a point of 2-power order): keeps the product invertible
+    else F::mul(d, x.zz, x.zzz);
+    store16(sc + 0, x.zz);
+    store16(sc + 1, x.zzz);
+    store16(sc + 2, run);                  // product of d_1 .. d_{j-1}
+    F::mul(run, run, d);
+  }
+  if (nwin < 2) return;
+  El rinv;
+  F::inv(rinv, run);
+  for (int j = nwin - 1; j >= 1; j--) {
+    El* sc = scratch + ((uint64_t)(j - 1) * npts + i) * 3;
+    El zz, zzz, pre, dinv, d;
+    load16_rw(zz, sc + 0);
+    load16_rw(zzz, sc + 1);
+    load16_rw(pre, sc + 2);
+    Affine<F> xy, o;
+    load16_rw(xy, tables + (uint64_t)j * npts + i);
+    if (F::is_zero(zz)) {
+      F::set_zero(o.x);
+      F::set_zero(o.y);
+      F::set_one(d);
+    } else {
+      F::mul(dinv, rinv, pre);             // 1 / (ZZ_j ZZZ_j)
+      El izz, izzz;
+      F::mul(izz, dinv, zzz);
+      F::mul(izzz, dinv, zz);
+      F::mul(o.x, xy.x, izz);
+      F::mul(o.y, xy.y, izzz);
+      F::mul(d, zz, zzz);
+    }
+    F::mul(rinv, rinv, d);
     store16(tables + (uint64_t)j * npts + i, o);
-    // continue from the normalised point: keeps the coordinates short-lived and exact
-    EC<F>::from_affine(x, o);
   }
 }
 
@@ -453,9 +495,17 @@ struct CurveImpl : CurveBackend {
     void* t = b.tables.get(std::max<uint64_t>(npts, 1) * b.nwin * pb);
     if (!npts) return;
     unsigned blocks = (unsigned)((npts + 63) / 64);
-    if (group == 1) k_build_tables<G1F><<<blocks, 64, 0, s>>>((const Affine<G1F>*)d_points, npts, b.c, b.nwin, (Affine<G1F>*)t);
-    else k_build_tables<G2F><<<blocks, 64, 0, s>>>((const Affine<G2F>*)d_points, npts, b.c, b.nwin, (Affine<G2F>*)t);
+    // scratch for the shared inversion: 3 coordinates per (window, point); freed (stream-ordered) after the kernel
+    DevBuf scratch;
+    void* sc = scratch.get(std::max<uint64_t>(npts * (uint64_t)(b.nwin - 1), 1) * 3 * (pb / 2));
+    if (group == 1)
+      k_build_tables<G1F><<<blocks, 64, 0, s>>>((const Affine<G1F>*)d_points, npts, b.c, b.nwin, (Affine<G1F>*)t,
+                                                (typename G1F::El*)sc);
+    else
+      k_build_tables<G2F><<<blocks, 64, 0, s>>>((const Affine<G2F>*)d_points, npts, b.c, b.nwin, (Affine<G2F>*)t,
+                                                (typename G2F::El*)sc);
     B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaStreamSynchronize(s));   // the scratch buffer is released on return
   }
 
   // ---------------------------------------------------------------- NTT
