@@ -26,7 +26,7 @@ struct CudaError : std::runtime_error {
 enum ProfTag { PROF_MSM_ACC_G1 = 0, PROF_MSM_ACC_G2 = 1, PROF_NTT_PASS = 2, PROF_MSM_TOTAL_G1 = 3, PROF_MSM_TOTAL_G2 = 4,
                PROF_TAGS = 5,   // tags below only appear in the timeline (b200_profile_timeline)
                PROF_MSM_SORT = 5, PROF_MSM_SCHED = 6, PROF_MSM_OVF = 7, PROF_MSM_BUCKET_REDUCE = 8, PROF_MSM_SUMS = 9,
-               PROF_INPUTS = 10, PROF_ASSEMBLE = 11, PROF_ALL_TAGS = 12 };
+               PROF_INPUTS = 10, PROF_ASSEMBLE = 11, PROF_MSM_PRE = 12, PROF_ALL_TAGS = 13 };
 void prof_count_launches(uint64_t n);
 uint64_t prof_launches();
 bool prof_enabled();
@@ -66,6 +66,7 @@ struct DevBuf {
 // blocks of whatever bulk kernel shares the GPU; ordering with the caller's stream is kept by events.
 struct MsmWorkspace {
   DevBuf hist, off, cur, sorted, chunk_sums, buckets, tasks, obuckets, partial, mid, groups, windows, ctr, perm, bins;
+  DevBuf pre_a, pre_b, pre_prefix, off2;   // affine pre-reduction (msm_pre.cuh)
   cudaStream_t tail = nullptr;
   cudaEvent_t e_fwd = nullptr, e_back = nullptr;
   void ensure_tail() {
@@ -170,7 +171,8 @@ struct CurveBackend {
   // ready for any stream that calls ws.wait_tail(stream)
   virtual void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out_xyzz,
                    MsmWorkspace& ws, cudaStream_t s, int c_override, MsmStats* stats,
-                   const uint32_t* d_index_map = nullptr, const MsmBases* bases = nullptr, bool join = true) = 0;
+                   const uint32_t* d_index_map = nullptr, const MsmBases* bases = nullptr, bool join = true,
+                   int pre = -1) = 0;   // pre: affine pre-reduction levels (table mode), -1 = default
   // Shared-scalar MSMs (table mode): ONE digit/sort pass over `n` scalars feeds up to 4 base sets, set j
   // taking point maps[j][i] for scalar i (0xffffffff = skip).  msm_reduce then accumulates and reduces
   // `count` consecutive sets (their tables in `bases`, all of `group`) into `count` XYZZ results; a G1 and a

@@ -3,6 +3,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "backend.h"
 #include "msm.cuh"
@@ -299,6 +300,8 @@ void msm_sort_launch(const void* d_scalars, const MsmPlan& pl, const MsmSets& se
   uint32_t* totals = chunk_sums + (uint64_t)pl.bwin * nchunks;
   const int tok_sort = prof_begin(PROF_MSM_SORT, s);
   B200_CUDA(cudaMemsetAsync(hist, 0, total_b * 4, s));
+  // pre-reduction: the padding slots of every bucket segment read as the point at infinity
+  if (pl.pre) B200_CUDA(cudaMemsetAsync(sorted, 0xff, (uint64_t)pl.bwin * pl.stride * 4, s));
   const auto* sc = reinterpret_cast<const typename Fr::El*>(d_scalars);
   const unsigned sblocks = (unsigned)((pl.n + 255) / 256);
   k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, sets);
@@ -343,15 +346,61 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   const int tok_sched = prof_begin(PROF_MSM_SCHED, s);
   B200_CUDA(cudaMemsetAsync(ctr, 0, sizeof(OvfCounters), s));
   B200_CUDA(cudaMemsetAsync(bins, 0, 2 * kSizeBins * 4, s));
+  // ---- affine pre-reduction (single bucket array): halve the sorted list pl.pre times, then accumulate the
+  //      reduced affine list directly
+  const uint32_t* off = so.off;
+  const uint32_t* end = so.end;
+  const uint32_t* totals = so.totals;
+  MsmPts acc_pts = pts;
+  const bool direct = pl.pre > 0;
+  if (direct) {
+    if (pl.bwin != 1 || !pl.table) throw std::runtime_error("msm: pre-reduction needs a single table-mode base set");
+    using El = typename F::El;
+    const uint64_t slots = pl.stride;                       // upper bound of the padded entry count
+    Affine<F>* bufA = (Affine<F>*)ws.pre_a.get((slots / 2 + 1) * sizeof(Affine<F>));
+    Affine<F>* bufB = pl.pre > 1 ? (Affine<F>*)ws.pre_b.get((slots / 4 + 1) * sizeof(Affine<F>)) : nullptr;
+    const Affine<F>* in = nullptr;
+    Affine<F>* out = bufA;
+    const int tok_pre = prof_begin(PROF_MSM_PRE, s);
+    for (int l = 0; l < pl.pre; l++) {
+      const uint64_t npairs = (slots >> l) / 2 + 1;
+      uint32_t per_thread = (uint32_t)std::min<uint64_t>(144, std::max<uint64_t>(8, npairs / (kPreThreads * 148ull * 8)));
+      const unsigned blocks = (unsigned)((npairs + (uint64_t)kPreThreads * per_thread - 1) / ((uint64_t)kPreThreads * per_thread));
+      El* prefix = (El*)ws.pre_prefix.get((uint64_t)blocks * kPreThreads * per_thread * sizeof(El));
+      if (l == 0)
+        k_msm_pre_round<F, true><<<blocks, kPreThreads, 0, s>>>((const Affine<F>*)pts.p[0], so.sorted, so.totals, 0,
+                                                                 per_thread, out, prefix);
+      else
+        k_msm_pre_round<F, false><<<blocks, kPreThreads, 0, s>>>(in, nullptr, so.totals, (uint32_t)l, per_thread, out, prefix);
+      in = out;
+      out = (out == bufA) ? bufB : bufA;
+    }
+    uint32_t* o2 = (uint32_t*)ws.off2.get((2 * total_b + 4) * 4);
+    uint32_t* e2 = o2 + total_b;
+    uint32_t* t2 = e2 + total_b;
+    k_msm_pre_offsets<<<(unsigned)((total_b + 255) / 256), 256, 0, s>>>(so.off, so.end, total_b, (uint32_t)pl.pre, o2, e2,
+                                                                         so.totals, t2, 1);
+    prof_end(tok_pre, s);
+    prof_count_launches(pl.pre + 1);
+    off = o2;
+    end = e2;
+    totals = t2;
+    acc_pts.p[0] = in;
+  }
   // size-sorted bucket schedule
   const unsigned szblocks = (unsigned)((total_b + kSizeThreads * kSizePerThread - 1) / (kSizeThreads * kSizePerThread));
-  k_msm_size_hist<<<szblocks, kSizeThreads, 0, s>>>(so.off, so.end, total_b, bins);
+  k_msm_size_hist<<<szblocks, kSizeThreads, 0, s>>>(off, end, total_b, bins);
   k_msm_size_scan<<<1, kSizeBins, 0, s>>>(bins, bins + kSizeBins);
-  k_msm_size_scatter<<<szblocks, kSizeThreads, 0, s>>>(so.off, so.end, total_b, bins + kSizeBins, perm);
+  k_msm_size_scatter<<<szblocks, kSizeThreads, 0, s>>>(off, end, total_b, bins + kSizeBins, perm);
   prof_end(tok_sched, s);
   const int tok_acc = prof_begin(GROUP == 2 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1, s);
-  k_msm_accumulate<F><<<(unsigned)((total_b + B200_ACC_THREADS - 1) / B200_ACC_THREADS), B200_ACC_THREADS, 0, s>>>(
-      pts, so.sorted, so.off, so.end, perm, so.totals, pl, buckets, obuckets, ctr);
+  const unsigned acc_blocks = (unsigned)((total_b + B200_ACC_THREADS - 1) / B200_ACC_THREADS);
+  if (direct)
+    k_msm_accumulate<F, true><<<acc_blocks, B200_ACC_THREADS, 0, s>>>(acc_pts, nullptr, off, end, perm, totals, pl, buckets,
+                                                                       obuckets, ctr);
+  else
+    k_msm_accumulate<F, false><<<acc_blocks, B200_ACC_THREADS, 0, s>>>(acc_pts, so.sorted, off, end, perm, totals, pl,
+                                                                        buckets, obuckets, ctr);
   prof_end(tok_acc, s);
   // ---- latency-bound tail on the high-priority stream
   ws.hop_to_tail(s);
@@ -360,7 +409,8 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   const int tok_ovf = prof_begin(PROF_MSM_OVF, t);
   k_msm_ovf_expand<<<148, 256, 0, t>>>(obuckets, ctr, pl, tasks);
   unsigned ovf_blocks = (unsigned)std::min<uint64_t>((pl.max_ovf + 127) / 128, 148 * 8);
-  k_msm_ovf_accumulate<F><<<ovf_blocks, 128, 0, t>>>(pts, so.sorted, pl, tasks, ctr, partial);
+  if (direct) k_msm_ovf_accumulate<F, true><<<ovf_blocks, 128, 0, t>>>(acc_pts, nullptr, pl, tasks, ctr, partial);
+  else k_msm_ovf_accumulate<F, false><<<ovf_blocks, 128, 0, t>>>(acc_pts, so.sorted, pl, tasks, ctr, partial);
   k_msm_ovf_merge_small<F><<<64, 64, 0, t>>>(obuckets, ctr, partial, buckets);
   const size_t merge_smem = kOvfMergeThreads * sizeof(Pt);
   k_msm_ovf_merge_l1<F><<<dim3(32, 64), kOvfMergeThreads, merge_smem, t>>>(obuckets, ctr, partial, mid);
@@ -413,10 +463,11 @@ struct CurveImpl : CurveBackend {
 
   void msm(int group, const void* d_points, const void* d_scalars, uint64_t n, void* d_out, MsmWorkspace& ws,
            cudaStream_t s, int c_override, MsmStats* stats, const uint32_t* d_index_map,
-           const MsmBases* bases, bool join) override {
+           const MsmBases* bases, bool join, int pre) override {
     if (bases && bases->group != group) throw std::runtime_error("msm: base tables belong to the other group");
     if (n >= (1ull << 31)) throw std::runtime_error("msm: n must be < 2^31");
-    MsmPlan pl = bases ? make_msm_plan_table(n, Fr::BITS, bases->c, bases->npts) : make_msm_plan(n, Fr::BITS, c_override);
+    MsmPlan pl = bases ? make_msm_plan_table(n, Fr::BITS, bases->c, bases->npts, 1, msm_pre_levels(n, bases->c, pre))
+                       : make_msm_plan(n, Fr::BITS, c_override);
     if (stats) *stats = MsmStats{pl.c, pl.nwin, pl.nb, pl.task, pl.group};
     if (n == 0) {
       B200_CUDA(cudaMemsetAsync(d_out, 0, xyzz_bytes(group), s));
@@ -436,6 +487,16 @@ struct CurveImpl : CurveBackend {
     msm_sort_launch<Fr>(d_scalars, pl, sets, ws, s, so);
     reduce_dispatch(group, so, pts, d_out, ws, s, join);
     prof_end(tok_total, s);
+  }
+
+  // affine pre-reduction levels for a table-mode MSM of n scalars: `want` < 0 = automatic (dense scalars assumed:
+  // one level per factor of two of the mean bucket load above 8, at most 3), B200_MSM_PRE overrides
+  static int msm_pre_levels(uint64_t n, int c, int want) {
+    const char* e = std::getenv("B200_MSM_PRE");   // read per call: the tests switch it
+    const int env = e ? std::atoi(e) : -1;
+    if (env >= 0) return std::min(env, 4);
+    if (want >= 0) return std::min(want, 4);
+    return 0;
   }
 
   void reduce_dispatch(int group, const MsmSorted& so, const MsmPts& pts, void* d_out, MsmWorkspace& ws,

@@ -15,6 +15,7 @@
 #pragma once
 #include "ec.cuh"
 #include "msm_plan.h"
+#include "msm_pre.cuh"
 
 namespace b200 {
 
@@ -131,8 +132,9 @@ k_msm_scan_sums(const uint32_t* __restrict__ hist, MsmPlan pl, uint32_t* __restr
   const uint32_t* h = hist + (uint64_t)blockIdx.y * pl.nb;
   const uint32_t first = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
   uint32_t sum = 0;
+  const uint32_t pad = (1u << pl.pre) - 1u;   // segments are padded to multiples of 2^pre (msm_pre.cuh)
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) sum += first + k < pl.nb ? h[first + k] : 0;
+  for (int k = 0; k < kScanItems; k++) sum += first + k < pl.nb ? ((h[first + k] + pad) & ~pad) : 0;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
   if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = sum;
@@ -177,9 +179,10 @@ k_msm_scan(const uint32_t* __restrict__ hist, MsmPlan pl, const uint32_t* __rest
   const uint32_t first = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   uint32_t sum = 0;
+  const uint32_t pad = (1u << pl.pre) - 1u;
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
-    v[k] = first + k < pl.nb ? h[first + k] : 0;
+    v[k] = first + k < pl.nb ? ((h[first + k] + pad) & ~pad) : 0;
     sum += v[k];
   }
   uint32_t x = sum;
@@ -292,23 +295,34 @@ struct MsmPts {
   const void* p[kMaxSets];
 };
 
-template <class F>
+// DIRECT: the run is `len` affine points stored contiguously at `points` (output of the affine pre-reduction);
+// otherwise `idx` holds (table index | sign) entries into `points`.
+template <class F, bool DIRECT>
+__device__ __forceinline__ void accumulate_fetch(Affine<F>& dst, uint32_t& e, const Affine<F>* __restrict__ points,
+                                                 const uint32_t* __restrict__ idx, uint32_t k) {
+  if (DIRECT) {
+    e = 0;
+    load16(dst, points + k);
+  } else {
+    e = idx[k];
+    load16(dst, points + (e & 0x7fffffffu));
+  }
+}
+
+template <class F, bool DIRECT>
 __device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const Affine<F>* __restrict__ points,
                                                const uint32_t* __restrict__ idx, uint32_t len) {
   using E = EC<F>;
   E::set_inf(acc);
   if (len == 0) return;
   // software pipeline: the next point is in flight while the current mixed add runs
-  uint32_t e = idx[0];
+  uint32_t e;
   Affine<F> nxt;
-  load16(nxt, points + (e & 0x7fffffffu));
+  accumulate_fetch<F, DIRECT>(nxt, e, points, idx, 0);
   for (uint32_t k = 0; k < len; k++) {
     Affine<F> cur = nxt;
     bool neg = e >> 31;
-    if (k + 1 < len) {
-      e = idx[k + 1];
-      load16(nxt, points + (e & 0x7fffffffu));
-    }
+    if (k + 1 < len) accumulate_fetch<F, DIRECT>(nxt, e, points, idx, k + 1);
     if (neg) E::neg(cur);
     E::madd(acc, cur);
   }
@@ -318,7 +332,7 @@ __device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const Affine<F>* __
 // iteration, so the (64 KB, larger than the instruction cache) loop body is streamed once per SM and
 // iteration instead of once per warp.  Buckets of a block have (almost) equal sizes thanks to the
 // size-sorted schedule, so the padding iterations are few.
-template <class F>
+template <class F, bool DIRECT>
 __device__ __forceinline__ void accumulate_run_lockstep(XYZZ<F>& acc, const Affine<F>* __restrict__ points,
                                                         const uint32_t* __restrict__ idx, uint32_t len) {
   using E = EC<F>;
@@ -331,19 +345,13 @@ __device__ __forceinline__ void accumulate_run_lockstep(XYZZ<F>& acc, const Affi
   const uint32_t trips = s_trips;
   uint32_t e = 0;
   Affine<F> nxt;
-  if (len) {
-    e = idx[0];
-    load16(nxt, points + (e & 0x7fffffffu));
-  }
+  if (len) accumulate_fetch<F, DIRECT>(nxt, e, points, idx, 0);
   for (uint32_t k = 0; k < trips; k++) {
     __syncthreads();
     if (k < len) {
       Affine<F> cur = nxt;
       bool neg = e >> 31;
-      if (k + 1 < len) {
-        e = idx[k + 1];
-        load16(nxt, points + (e & 0x7fffffffu));
-      }
+      if (k + 1 < len) accumulate_fetch<F, DIRECT>(nxt, e, points, idx, k + 1);
       if (neg) E::neg(cur);
       E::madd(acc, cur);
     }
@@ -433,7 +441,7 @@ template <class F>
 struct AccCfg {
   static constexpr int kMinBlocks = sizeof(typename F::El) >= 96 ? B200_ACC_MIN_BLOCKS_BIG : B200_ACC_MIN_BLOCKS;
 };
-template <class F>
+template <class F, bool DIRECT>
 __global__ void __launch_bounds__(B200_ACC_THREADS, AccCfg<F>::kMinBlocks)
 k_msm_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ off,
                  const uint32_t* __restrict__ end, const uint32_t* __restrict__ perm,
@@ -462,13 +470,15 @@ k_msm_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, const uint32_t
     }
     // else: cannot happen (capacity covers every entry); stay correct anyway by taking the whole bucket
   }
-  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[pl.table ? w : 0]);
+  // DIRECT: pts.p[0] is the pre-reduced affine list (single bucket array), `start` indexes it
+  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[pl.table ? w : 0]) + (DIRECT ? start : 0);
+  const uint32_t* idx = DIRECT ? nullptr : sorted + (uint64_t)w * pl.stride + start;
   XYZZ<F> acc;
 #ifdef B200_ACC_LOCKSTEP
-  accumulate_run_lockstep<F>(acc, points, sorted + (uint64_t)w * pl.stride + start, mine);
+  accumulate_run_lockstep<F, DIRECT>(acc, points, idx, mine);
   if (valid) store16(buckets + gb, acc);
 #else
-  accumulate_run<F>(acc, points, sorted + (uint64_t)w * pl.stride + start, mine);
+  accumulate_run<F, DIRECT>(acc, points, idx, mine);
   store16(buckets + gb, acc);
 #endif
 }
@@ -491,7 +501,7 @@ k_msm_ovf_expand(const OvfBucket* __restrict__ obuckets, const OvfCounters* __re
   }
 }
 
-template <class F>
+template <class F, bool DIRECT>
 __global__ void __launch_bounds__(128)
 k_msm_ovf_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, MsmPlan pl,
                      const OvfTask* __restrict__ tasks, const OvfCounters* __restrict__ ctr,
@@ -500,9 +510,9 @@ k_msm_ovf_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, MsmPlan pl
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     OvfTask tk = tasks[t];
     uint32_t w = tk.bucket / pl.nb;
-    const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[pl.table ? w : 0]);
+    const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[pl.table ? w : 0]) + (DIRECT ? tk.start : 0);
     XYZZ<F> acc;
-    accumulate_run<F>(acc, points, sorted + (uint64_t)w * pl.stride + tk.start, tk.len);
+    accumulate_run<F, DIRECT>(acc, points, DIRECT ? nullptr : sorted + (uint64_t)w * pl.stride + tk.start, tk.len);
     store16(partial + t, acc);
   }
 }

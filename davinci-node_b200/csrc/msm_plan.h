@@ -24,6 +24,7 @@ struct MsmPlan {
   int nwin;            // digit windows = ceil((scalar_bits + 1) / c)
   int bwin;            // bucket arrays: nwin (windowed) or the number of base sets (table mode)
   int table;           // 1 = table mode
+  int pre;             // affine pre-reduction levels (msm_pre.cuh): bucket segments are padded to multiples of 2^pre
   uint32_t nb;         // buckets per bucket window = 2^(c-1)
   uint32_t task;       // max points a single thread accumulates for one bucket
   uint32_t task_min;   // lower bound of the load-adaptive cap
@@ -85,7 +86,7 @@ inline void msm_plan_finish(MsmPlan& pl) {
   pl.group = std::min<uint32_t>(g, pl.nb);
   // every overflowing bucket holds > task_min points and every overflow task but the last is full
   pl.max_ovf = (uint32_t)((adds / pl.ovf_task + adds / pl.task_min + 2) * (pl.table ? pl.bwin : 1));
-  pl.stride = pl.table ? adds : pl.n;
+  pl.stride = pl.table ? adds + ((uint64_t)pl.nb << pl.pre) : pl.n;
 }
 
 inline MsmPlan make_msm_plan(uint64_t n, int scalar_bits, int c_override) {
@@ -112,9 +113,10 @@ inline MsmPlan make_msm_plan(uint64_t n, int scalar_bits, int c_override) {
   return pl;
 }
 
-inline MsmPlan make_msm_plan_table(uint64_t n, int scalar_bits, int c, uint64_t npts, int nsets = 1) {
+inline MsmPlan make_msm_plan_table(uint64_t n, int scalar_bits, int c, uint64_t npts, int nsets = 1, int pre = 0) {
   MsmPlan pl{};
   pl.n = n;
+  pl.pre = nsets == 1 ? pre : 0;
   pl.c = c;
   pl.nwin = msm_nwin(scalar_bits, c);
   pl.bwin = nsets;

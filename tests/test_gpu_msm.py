@@ -141,3 +141,43 @@ def test_msm_table_mode(env, cname, group):
             assert L.dec_affine(oa.cpu().numpy(), group)[0] == want2
         finally:
             capi.check(capi.lib.b200_bases_release(h.value))
+
+
+@pytest.mark.parametrize("levels", [1, 2, 3])
+@pytest.mark.parametrize("cname,group", [("bls12_377", 1), ("bls12_377", 2), ("bn254", 1), ("bw6_761", 1)])
+def test_msm_affine_pre_reduction(env, cname, group, levels, monkeypatch):
+    """Table-mode MSM with the sorted entries halved `levels` times by batched affine additions (shared inversion)
+    before the bucket accumulation: same result as the oracle, including repeated points (doubling inside a pair),
+    P + (-P) pairs, infinity points, a heavily loaded bucket and buckets shorter than the padding."""
+    import ctypes as C
+    from gpu_util import rand_points, to_dev, dev_empty, ptr, stream, sync
+    capi, layout = env
+    L = layout.Layout(cname)
+    cx = ocurve.ctx(cname)
+    G = cx.group(group)
+    rnd = random.Random(100 * levels + group)
+    n = 700
+    pts = rand_points(cx, group, 40, rnd)
+    pts = [pts[rnd.randrange(40)] for _ in range(n)]          # many repeated points
+    pts[11] = None
+    sc = [rnd.randrange(cx.r) for _ in range(n)]
+    for i in range(0, 200):                                     # equal scalars on repeated points: P + P and P + (-P)
+        sc[i] = 5 if i % 3 else cx.r - 5
+    for i in range(200, 300):
+        sc[i] = 1
+    sc[300], sc[301] = 0, cx.r - 1
+    want = G.msm(pts, sc)
+    dp = to_dev(L.enc_affine(pts, group))
+    ds = to_dev(L.enc_fr(sc))
+    monkeypatch.setenv("B200_MSM_PRE", str(levels))
+    for c in (4, 9):
+        h = C.c_uint64(0)
+        capi.check(capi.lib.b200_bases_create_dev(L.id, group, ptr(dp), n, c, C.byref(h), stream()))
+        try:
+            ox, oa = dev_empty(L.xyzz_bytes(group)), dev_empty(L.affine_bytes(group))
+            capi.check(capi.lib.b200_msm_bases_dev(h.value, ptr(ds), n, None, ptr(ox), stream()))
+            capi.check(capi.lib.b200_to_affine_dev(L.id, group, ptr(ox), ptr(oa), 1, stream()))
+            sync()
+            assert L.dec_affine(oa.cpu().numpy(), group)[0] == want, (cname, group, c, levels)
+        finally:
+            capi.check(capi.lib.b200_bases_release(h.value))

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 TAGS = {0: "acc_g1", 1: "acc_g2", 2: "ntt_pass", 3: "msm_total_g1", 4: "msm_total_g2", 5: "sort", 6: "sched",
-        7: "ovf", 8: "bucket_reduce", 9: "sums", 10: "inputs", 11: "assemble"}
+        7: "ovf", 8: "bucket_reduce", 9: "sums", 10: "inputs", 11: "assemble", 12: "pre_reduce"}
 
 
 def union(iv):
