@@ -206,6 +206,10 @@ struct CurveBackend {
   virtual void kzg_roots(void* d_roots, uint32_t n, cudaStream_t s) = 0;
   virtual void kzg_open(const void* d_p, const void* d_roots, const void* d_z_be, uint32_t n, void* d_q, void* d_y_bytes,
                         void* d_scratch, uint32_t* d_err, cudaStream_t s) = 0;
+  // cell proofs (EIP-7594): a_k table, and the 128 quotients p div (X^m - a_k) from the coefficient form
+  virtual void kzg_cell_shifts(void* d_shifts, uint32_t ncells, uint32_t m, uint32_t n, cudaStream_t s) = 0;
+  virtual void kzg_cell_quotients(const void* d_coeffs, const void* d_shifts, void* d_q, uint32_t n, uint32_t m,
+                                  uint32_t ncells, cudaStream_t s) = 0;
   // --- point helpers
   virtual void to_affine(int group, const void* d_xyzz, void* d_affine, uint32_t count, cudaStream_t s) = 0;
   // affine(sum of count XYZZ points): combine of range-split MSM partials

@@ -430,6 +430,34 @@ int b200_blob_commit(uint64_t h, const uint8_t* blob, uint8_t commitment_out[48]
   });
 }
 
+int b200_kzg_srs_add_monomial(uint64_t h, const uint8_t* g1_monomial, uint32_t npoints) {
+  return guarded([&] {
+    if (!g1_monomial) throw std::runtime_error("null argument");
+    std::shared_ptr<KzgSrsDev> srs;
+    {
+      std::lock_guard<std::mutex> lk(g_hmu);
+      auto it = g_srs.find(h);
+      if (it == g_srs.end()) throw std::runtime_error("unknown SRS handle");
+      srs = it->second;
+    }
+    srs->add_monomial(g1_monomial, npoints);
+  });
+}
+
+int b200_blob_cell_proofs(uint64_t h, const uint8_t* blob, uint8_t* proofs_out, int device) {
+  return guarded([&] {
+    if (!blob || !proofs_out) throw std::runtime_error("null argument");
+    std::shared_ptr<KzgSrsDev> srs;
+    {
+      std::lock_guard<std::mutex> lk(g_hmu);
+      auto it = g_srs.find(h);
+      if (it == g_srs.end()) throw std::runtime_error("unknown SRS handle");
+      srs = it->second;
+    }
+    srs->blob_cell_proofs(blob, proofs_out, device);
+  });
+}
+
 int b200_blob_proof(uint64_t h, const uint8_t* blob, const uint8_t point_be[32], uint8_t proof_out[48],
                     uint8_t claim_out[32], int device) {
   return guarded([&] {

@@ -727,6 +727,28 @@ struct CurveImpl : CurveBackend {
     }
   }
 
+  void kzg_cell_shifts(void* d_shifts, uint32_t ncells, uint32_t m, uint32_t n, cudaStream_t s) override {
+    if constexpr (Cfg::ID == 3) {
+      int log_ext = 0;
+      while ((1u << log_ext) < 2 * n) log_ext++;
+      k_kzg_cell_shifts<Fr><<<(ncells + 63) / 64, 64, 0, s>>>((FrEl*)d_shifts, ncells, m, log_ext);
+      B200_CUDA(cudaGetLastError());
+    } else {
+      throw std::runtime_error("kzg_cell_shifts: only BLS12-381 is supported");
+    }
+  }
+  void kzg_cell_quotients(const void* d_coeffs, const void* d_shifts, void* d_q, uint32_t n, uint32_t m, uint32_t ncells,
+                          cudaStream_t s) override {
+    if constexpr (Cfg::ID == 3) {
+      k_kzg_cell_quotients<Fr><<<(ncells * m + 127) / 128, 128, 0, s>>>((const FrEl*)d_coeffs, (const FrEl*)d_shifts,
+                                                                         (FrEl*)d_q, n, m, ncells);
+      prof_count_launches(1);
+      B200_CUDA(cudaGetLastError());
+    } else {
+      throw std::runtime_error("kzg_cell_quotients: only BLS12-381 is supported");
+    }
+  }
+
   void scale_vec(void* d_x, const void* d_c, uint64_t n, cudaStream_t s) override {
     if (!n) return;
     k_scale_vec<Fr><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((FrEl*)d_x, (const FrEl*)d_c, n);

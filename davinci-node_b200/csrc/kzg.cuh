@@ -310,4 +310,53 @@ __global__ void k_kzg_open_fix(const typename Fr::El* __restrict__ partial2, uin
   q[*hit] = s;
 }
 
+// ------------------------------------------------------------------------------------ cell proofs (EIP-7594)
+// proof_k = MSM(q_k, monomial SRS), q_k = p(X) div (X^m - a_k), a_k = h_k^m, h_k = w_2n^brp(m k): replaces go-ethereum
+// `kzg4844.ComputeCellProofs` (/root/reference/types/blobs.go:99-105).
+// shifts[k] = a_k for k < ncells  (m = cell size, a power of two; n = blob size)
+template <class Fr>
+__global__ void k_kzg_cell_shifts(typename Fr::El* __restrict__ shifts, uint32_t ncells, uint32_t m, int log_ext) {
+  using El = typename Fr::El;
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= ncells) return;
+  constexpr uint32_t g32[8] = {0x439f0d2bu, 0x3829971fu, 0x8c2280b9u, 0xb6368350u,
+                               0x22c813b4u, 0xd09b6819u, 0xdfe81f20u, 0x16a2a19eu};
+  El w, acc;
+#pragma unroll
+  for (int i = 0; i < 8; i++) w.v[i] = g32[i];
+  Fr::to_mont(w, w);
+  for (int i = 0; i < 32 - log_ext; i++) Fr::sqr(w, w);      // primitive 2n-th root
+  uint32_t e = __brev(m * k) >> (32 - log_ext);
+  Fr::set_one(acc);
+  while (e) {
+    if (e & 1) Fr::mul(acc, acc, w);
+    e >>= 1;
+    if (e) Fr::sqr(w, w);
+  }
+  for (uint32_t t = 1; t < m; t <<= 1) Fr::sqr(acc, acc);    // h^m
+  shifts[k] = acc;
+}
+
+// thread (k, r): the residue class r mod m of quotient k, from the top down: q[j] = c[j + m] + a_k q[j + m]
+template <class Fr>
+__global__ void k_kzg_cell_quotients(const typename Fr::El* __restrict__ coeffs, const typename Fr::El* __restrict__ shifts,
+                                     typename Fr::El* __restrict__ q, uint32_t n, uint32_t m, uint32_t ncells) {
+  using El = typename Fr::El;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncells * m) return;
+  const uint32_t k = t / m, r = t % m;
+  const El a = shifts[k];
+  El* out = q + (uint64_t)k * n;
+  El run, zero;
+  Fr::set_zero(run);
+  Fr::set_zero(zero);
+  for (int64_t j = (int64_t)n - m + r; j >= (int64_t)(n - m); j -= m) out[j] = zero;   // degree >= n - m: zero
+  for (int64_t j = (int64_t)n - 2 * m + r; j >= 0; j -= m) {
+    El c = coeffs[j + m];
+    Fr::mul(run, run, a);
+    Fr::add(run, run, c);
+    out[j] = run;
+  }
+}
+
 }  // namespace b200

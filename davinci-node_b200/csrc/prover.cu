@@ -444,6 +444,81 @@ std::unique_ptr<KzgSrsDev> KzgSrsDev::create(const uint8_t* g1_lagrange_compress
 KzgSrsDev::Inst::~Inst() {
   cudaSetDevice(device);
   if (st) cudaStreamDestroy(st);
+  for (auto& l : lane)
+    if (l) cudaStreamDestroy(l);
+  for (auto& e : lane_ev)
+    if (e) cudaEventDestroy(e);
+  if (fork_ev) cudaEventDestroy(fork_ev);
+}
+
+void KzgSrsDev::add_monomial(const uint8_t* g1_monomial_compressed, uint32_t n) {
+  if (n != npoints) throw std::runtime_error("monomial SRS must have as many points as the Lagrange SRS");
+  if (npoints < 2 * kCellSize) throw std::runtime_error("SRS too small for cell proofs");
+  for (auto& in : inst) {
+    std::lock_guard<std::mutex> lk(in->mu);
+    DeviceScope ds(in->device);
+    const size_t g1b = cb->affine_bytes(1), frb = cb->fr_bytes();
+    DevBuf raw, pts;
+    upload(raw, g1_monomial_compressed, (size_t)n * 48, in->st);
+    pts.get((size_t)n * g1b);
+    uint32_t* err = (uint32_t*)in->err.p;
+    B200_CUDA(cudaMemsetAsync(err, 0, 4, in->st));
+    cb->g1_decompress(raw.p, pts.p, n, err, in->st);
+    cb->build_tables(in->mono, 1, pts.p, n, 0, in->st);
+    uint32_t herr = 0;
+    B200_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, in->st));
+    B200_CUDA(cudaStreamSynchronize(in->st));
+    if (herr) throw std::runtime_error("monomial SRS contains an invalid compressed G1 point");
+    // evaluation domain of the blob (omega = roots[n/2] since roots[i] = omega^brp(i); the coset generator is unused)
+    const uint8_t* roots = (const uint8_t*)in->roots.p;
+    cb->domain_init(in->dom, ilog2_exact(npoints), roots + (size_t)(npoints / 2) * frb, roots + frb, in->st);
+    cb->kzg_cell_shifts(in->shifts.get((size_t)kCells * frb), kCells, kCellSize, npoints, in->st);
+    in->cellq.get((size_t)kCells * npoints * frb);
+    in->cell_xyzz.get((size_t)kCells * cb->xyzz_bytes(1));
+    in->cell_out.get((size_t)kCells * (g1b + 48));
+    for (int l = 0; l < Inst::kCellLanes; l++) {
+      if (!in->lane[l]) B200_CUDA(cudaStreamCreateWithFlags(&in->lane[l], cudaStreamNonBlocking));
+      if (!in->lane_ev[l]) B200_CUDA(cudaEventCreateWithFlags(&in->lane_ev[l], cudaEventDisableTiming));
+    }
+    if (!in->fork_ev) B200_CUDA(cudaEventCreateWithFlags(&in->fork_ev, cudaEventDisableTiming));
+    B200_CUDA(cudaStreamSynchronize(in->st));
+    in->have_mono = true;
+  }
+}
+
+void KzgSrsDev::blob_cell_proofs(const uint8_t* blob, uint8_t* proofs, int device) {
+  Inst* I = &pick(device);
+  std::lock_guard<std::mutex> lk(I->mu);
+  if (!I->have_mono) throw std::runtime_error("cell proofs need the monomial SRS (b200_kzg_srs_add_monomial)");
+  DeviceScope ds(I->device);
+  const size_t g1b = cb->affine_bytes(1), x1 = cb->xyzz_bytes(1), frb = cb->fr_bytes();
+  uint32_t* err = (uint32_t*)I->err.p;
+  B200_CUDA(cudaMemsetAsync(err, 0, 4, I->st));
+  B200_CUDA(cudaMemcpyAsync(I->blob.p, blob, (size_t)npoints * 32, cudaMemcpyHostToDevice, I->st));
+  cb->blob_to_scalars(I->blob.p, I->scalars.p, npoints, err, I->st);
+  // evaluations in bit-reversed order -> coefficients: inverse DIT transform (bit-reversed in, natural out, 1/n)
+  cb->ntt(I->dom, I->scalars.p, true, true, false, I->st);
+  cb->kzg_cell_quotients(I->scalars.p, I->shifts.p, I->cellq.p, npoints, kCellSize, kCells, I->st);
+  B200_CUDA(cudaEventRecord(I->fork_ev, I->st));
+  uint8_t* xyzz = (uint8_t*)I->cell_xyzz.p;
+  for (int l = 0; l < Inst::kCellLanes; l++) B200_CUDA(cudaStreamWaitEvent(I->lane[l], I->fork_ev, 0));
+  for (uint32_t k = 0; k < kCells; k++) {
+    const int l = k % Inst::kCellLanes;
+    cb->msm(1, nullptr, (const uint8_t*)I->cellq.p + (size_t)k * npoints * frb, npoints, xyzz + (size_t)k * x1,
+            I->lane_ws[l], I->lane[l], 0, nullptr, nullptr, &I->mono);
+  }
+  for (int l = 0; l < Inst::kCellLanes; l++) {
+    B200_CUDA(cudaEventRecord(I->lane_ev[l], I->lane[l]));
+    B200_CUDA(cudaStreamWaitEvent(I->st, I->lane_ev[l], 0));
+  }
+  uint8_t* o = (uint8_t*)I->cell_out.p;
+  cb->to_affine(1, xyzz, o, kCells, I->st);
+  cb->g1_compress(o, o + (size_t)kCells * g1b, kCells, I->st);
+  uint32_t herr = 0;
+  B200_CUDA(cudaMemcpyAsync(proofs, o + (size_t)kCells * g1b, (size_t)kCells * 48, cudaMemcpyDeviceToHost, I->st));
+  B200_CUDA(cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, I->st));
+  B200_CUDA(cudaStreamSynchronize(I->st));
+  if (herr) throw std::runtime_error("blob contains a non-canonical field element (>= BLS12-381 r)");
 }
 
 KzgSrsDev::Inst& KzgSrsDev::pick(int device) {

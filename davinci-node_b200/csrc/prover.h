@@ -67,6 +67,16 @@ struct KzgSrsDev {
     MsmBases tables;
     DevBuf brp, blob, scalars, out, err, roots, quot, scratch, zbuf;
     MsmWorkspace ws;
+    // cell proofs: monomial-basis tables, a_k table, 128 quotients, proofs; the 128 MSMs rotate over kCellLanes streams
+    static constexpr int kCellLanes = 8;
+    MsmBases mono;
+    bool have_mono = false;
+    NttDomain dom;
+    DevBuf shifts, cellq, cell_xyzz, cell_out;
+    cudaStream_t lane[kCellLanes] = {};
+    cudaEvent_t lane_ev[kCellLanes] = {};
+    cudaEvent_t fork_ev = nullptr;
+    MsmWorkspace lane_ws[kCellLanes];
     ~Inst();
   };
   CurveBackend* cb = nullptr;
@@ -78,6 +88,11 @@ struct KzgSrsDev {
   void blob_commit(const uint8_t* blob, uint8_t* commitment48, int device);
   // KZG opening at z (32 big-endian bytes): 48-byte proof and the claimed value y = p(z) (32 big-endian bytes)
   void blob_proof(const uint8_t* blob, const uint8_t* z32, uint8_t* proof48, uint8_t* y32, int device);
+  // monomial-basis G1 points [tau^j]_1 (compressed, j < npoints): needed by the cell proofs
+  void add_monomial(const uint8_t* g1_monomial_compressed, uint32_t n);
+  // EIP-7594 cell proofs: 128 x 48 bytes
+  void blob_cell_proofs(const uint8_t* blob, uint8_t* proofs, int device);
+  static constexpr uint32_t kCells = 128, kCellSize = 64;
   Inst& pick(int device);
 };
 

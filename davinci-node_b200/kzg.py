@@ -22,8 +22,9 @@ class BlobError(ValueError):
     pass
 
 
-def load_trusted_setup(g1_lagrange_compressed: bytes):
-    """g1_lagrange_compressed: 4096 * 48 bytes.  (Go: parsed from config.KZGTrustedSetup.)"""
+def load_trusted_setup(g1_lagrange_compressed: bytes, g1_monomial_compressed: bytes = None):
+    """g1_lagrange_compressed: 4096 * 48 bytes; g1_monomial_compressed (optional, same size): the monomial-basis
+    points, needed by ComputeCellProofs.  (Go: parsed from config.KZGTrustedSetup.)"""
     global _srs_handle
     with _lock:
         capi.init_once()
@@ -32,6 +33,9 @@ def load_trusted_setup(g1_lagrange_compressed: bytes):
             raise BlobError("SRS must be a whole number of 48-byte points")
         h = C.c_uint64(0)
         capi.check(capi.lib.b200_kzg_srs_register(buf.ctypes.data, len(buf) // 48, C.byref(h)))
+        if g1_monomial_compressed is not None:
+            mono = np.frombuffer(g1_monomial_compressed, dtype=np.uint8).copy()
+            capi.check(capi.lib.b200_kzg_srs_add_monomial(h.value, mono.ctypes.data, len(mono) // 48))
         if _srs_handle is not None:
             capi.check(capi.lib.b200_kzg_srs_release(_srs_handle))
         _srs_handle = h.value
@@ -86,3 +90,15 @@ class Blob:
         data = b"FSBLOBVERIFY_V1_" + (BLOB_BYTES // 32).to_bytes(16, "big") + self.data + bytes(commitment)
         z = int.from_bytes(hashlib.sha256(data).digest(), "big") % BLS_MODULUS
         return self.ComputeProof(z, device)[0]
+
+    def ComputeCellProofs(self, device=-1):
+        """types/blobs.go:99: the 128 EIP-7594 cell proofs (48 bytes each)."""
+        if _srs_handle is None:
+            raise BlobError("trusted setup not loaded (call load_trusted_setup first)")
+        blob = np.frombuffer(self.data, dtype=np.uint8)
+        out = np.zeros(128 * 48, dtype=np.uint8)
+        try:
+            capi.check(capi.lib.b200_blob_cell_proofs(_srs_handle, blob.ctypes.data, out.ctypes.data, device))
+        except capi.B200Error as e:
+            raise BlobError(str(e)) from e
+        return [bytes(out[48 * k:48 * (k + 1)]) for k in range(128)]

@@ -178,6 +178,12 @@ B200_API int b200_blob_commit(uint64_t srs, const uint8_t* blob /* npoints*32 by
  * sha256("FSBLOBVERIFY_V1_" || u128(4096) || blob || commitment) mod r, computed by the host shim, it is
  * gethkzg.ComputeBlobProof (types/blobs.go:111-117).  Points inside the evaluation domain are handled as in
  * EIP-4844 compute_quotient_eval_within_domain. */
+/* EIP-7594 cell proofs.  b200_kzg_srs_add_monomial registers the ceremony's monomial-basis points [tau^j]_1
+ * (npoints x 48-byte compressed, the third block of config/kzg_trusted_setup.txt); b200_blob_cell_proofs then writes
+ * the 128 x 48-byte proofs of the blob's cells: inverse NTT to coefficients, the 128 quotients by X^64 - h_k^64 and
+ * 128 MSMs on the GPU.  Replaces gethkzg.ComputeCellProofs (types/blobs.go:99-105). */
+B200_API int b200_kzg_srs_add_monomial(uint64_t srs, const uint8_t* g1_monomial, uint32_t npoints);
+B200_API int b200_blob_cell_proofs(uint64_t srs, const uint8_t* blob, uint8_t* proofs_out /* 128*48 bytes */, int device);
 B200_API int b200_blob_proof(uint64_t srs, const uint8_t* blob, const uint8_t point_be[32], uint8_t proof_out[48],
                              uint8_t claim_out[32], int device);
 

@@ -134,3 +134,50 @@ def compute_challenge(blob: bytes, commitment: bytes) -> int:
 
 def compute_blob_proof(blob: bytes, commitment: bytes, lagrange_points) -> bytes:
     return compute_proof(blob, compute_challenge(blob, commitment), lagrange_points)[0]
+
+
+# ----------------------------------------------------------------------------- cell proofs (EIP-7594)
+# Restates go-ethereum `kzg4844.ComputeCellProofs` (called at /root/reference/types/blobs.go:99-105) =
+# `compute_cells_and_kzg_proofs` of consensus-specs fulu/polynomial-commitments-sampling.md: the blob polynomial in
+# coefficient form is divided by the vanishing polynomial X^64 - h_k^64 of each of the 128 cosets of the extended
+# (8192-point) domain; proof_k commits to the quotient in the MONOMIAL basis of the ceremony.
+CELLS_PER_EXT_BLOB = 128
+FIELD_ELEMENTS_PER_CELL = 64
+
+
+def blob_coefficients(vals):
+    """evaluations over the 4096th roots of unity in bit-reversed order -> monomial coefficients."""
+    dom = N.Domain(P.BLS12_381, len(vals))
+    return N.fft(list(vals), dom, inverse=True, dit=True)
+
+
+def cell_coset_shift(k, n=4096):
+    """h_k: first element of coset k = roots_of_unity_brp(2n)[64 k]."""
+    r = P.BLS12_381.r
+    ext = 2 * n
+    logext = ext.bit_length() - 1
+    w = pow(PRIMITIVE_ROOT_2_32, 1 << (32 - logext), r)
+    return pow(w, N.bitrev(FIELD_ELEMENTS_PER_CELL * k, logext), r)
+
+
+def cell_quotient(coeffs, k):
+    """quotient of p(X) by X^64 - h_k^64 (remainder = the interpolant of the cell, discarded)."""
+    r = P.BLS12_381.r
+    m = FIELD_ELEMENTS_PER_CELL
+    a = pow(cell_coset_shift(k, len(coeffs)), m, r)
+    n = len(coeffs)
+    q = [0] * (n - m)
+    for j in range(n - m - 1, -1, -1):
+        q[j] = (coeffs[j + m] + (a * q[j + m] if j + m < n - m else 0)) % r
+    return q
+
+
+def compute_cell_proofs(blob: bytes, monomial_points, cells=None):
+    """-> {cell index: 48-byte proof} for `cells` (default all 128); monomial_points = [tau^j]_1, j < 4096."""
+    cx = C.ctx("bls12_381")
+    coeffs = blob_coefficients(blob_scalars(blob))
+    out = {}
+    for k in (range(CELLS_PER_EXT_BLOB) if cells is None else cells):
+        q = cell_quotient(coeffs, k)
+        out[k] = g1_compress(cx.G1.msm(monomial_points[:len(q)], q))
+    return out

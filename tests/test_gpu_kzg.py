@@ -115,3 +115,24 @@ def test_opening_point_must_be_canonical(kz):
         kz.Blob(blob).ComputeProof(1 << 256)
     proof, y = kz.Blob(blob).ComputeProof(5)           # zero polynomial: quotient 0 -> point at infinity, y = 0
     assert y == 0 and proof == bytes([0xC0]) + bytes(47)
+
+
+def test_cell_proofs_vs_oracle(kz):
+    """Blob.ComputeCellProofs (types/blobs.go:99): 128 proofs; the committed vectors (cells 0, 1, 77, 127 of the
+    reference's sample blob) and the oracle on a statetransition-shaped blob (cells 5 and 126) must match, and the
+    zero blob gives 128 points at infinity."""
+    mono_raw = open(os.path.join(GOLD, "kzg_g1_monomial.bin"), "rb").read()
+    kz.load_trusted_setup(open(os.path.join(GOLD, "kzg_g1_lagrange.bin"), "rb").read(), mono_raw)
+    kat = json.load(open(os.path.join(GOLD, "kzg_cell_kat.json")))
+    proofs = kz.Blob(_blob("blobdata1")).ComputeCellProofs()
+    assert len(proofs) == 128
+    for k, want in kat["proofs"].items():
+        assert proofs[int(k)].hex() == want, k
+    mono = [OK.g1_decompress(mono_raw[i:i + 48]) for i in range(0, len(mono_raw), 48)]
+    rnd = random.Random(23)
+    cells = [rnd.randrange(OP.BN254.r) for _ in range(2193)] + [0] * (4096 - 2193)
+    blob = b"".join(v.to_bytes(32, "big") for v in cells)
+    got = kz.Blob(blob).ComputeCellProofs()
+    want = OK.compute_cell_proofs(blob, mono, cells=[5, 126])
+    assert got[5] == want[5] and got[126] == want[126]
+    assert kz.Blob(bytes(4096 * 32)).ComputeCellProofs() == [bytes([0xC0]) + bytes(47)] * 128

@@ -78,3 +78,60 @@ def test_fiat_shamir_challenge_layout():
     com = bytes([0xC0]) + bytes(47)
     want = int.from_bytes(hashlib.sha256(b"FSBLOBVERIFY_V1_" + bytes(14) + b"\x10\x00" + blob + com).digest(), "big")
     assert K.compute_challenge(blob, com) == want % P.BLS12_381.r
+
+
+def test_cell_quotient_matches_interpolation_definition():
+    """EIP-7594 cell proofs (types/blobs.go:99 ComputeCellProofs): the oracle's quotient q_k = p div (X^64 - h_k^64)
+    must satisfy q_k(t) = (p(t) - I_k(t)) / Z_k(t) at a random t, with I_k the Lagrange interpolant of p over the
+    spec's coset k (bit-reversed 8192-point domain) computed independently from the evaluations."""
+    import random
+    r = P.BLS12_381.r
+    rnd = random.Random(31)
+    n = 4096
+    coef = [rnd.randrange(r) for _ in range(n)]
+    ev = lambda x: sum(c * pow(x, k, r) for k, c in enumerate(coef)) % r
+    dom = N.Domain(P.BLS12_381, n)
+    cells = N.bit_reverse_list(N.dft_natural(coef, dom.omega, r))
+    assert K.blob_coefficients(cells) == coef
+    t = rnd.randrange(r)
+    pt = ev(t)
+    w8192 = pow(7, (r - 1) // 8192, r)                     # the spec's compute_roots_of_unity(8192)
+    for k in (0, 1, 127):
+        coset = [pow(w8192, N.bitrev(64 * k + i, 13), r) for i in range(64)]
+        assert coset[0] == K.cell_coset_shift(k)
+        ys = [ev(z) for z in coset]
+        interp = 0
+        for i, (zi, yi) in enumerate(zip(coset, ys)):
+            num = den = 1
+            for j, zj in enumerate(coset):
+                if i != j:
+                    num = num * (t - zj) % r
+                    den = den * (zi - zj) % r
+            interp = (interp + yi * num * pow(den, -1, r)) % r
+        zt = (pow(t, 64, r) - pow(coset[0], 64, r)) % r
+        q = K.cell_quotient(coef, k)
+        assert len(q) == n - 64
+        assert sum(c * pow(t, j, r) for j, c in enumerate(q)) % r == (pt - interp) * pow(zt, -1, r) % r
+
+
+def test_cell_proof_known_answers_and_commitment_identity():
+    """The committed cell-proof vectors (tools/make_golden.py) are reproduced, and on the REAL ceremony points the
+    proof of cell 1 satisfies  C = [q(tau) tau^64] - a [q(tau)] + [I(tau)]  in G1 (p = q Z + I with Z = X^64 - a),
+    all three terms from the monomial basis, C from the Lagrange basis."""
+    cx = C.ctx("bls12_381")
+    r = P.BLS12_381.r
+    raw = open(os.path.join(GOLD, "kzg_g1_monomial.bin"), "rb").read()
+    mono = [K.g1_decompress(raw[i:i + 48]) for i in range(0, len(raw), 48)]
+    blob = open(os.path.join(GOLD, "blobdata1.bin"), "rb").read()
+    kat = json.load(open(os.path.join(GOLD, "kzg_cell_kat.json")))
+    k = 1
+    proofs = K.compute_cell_proofs(blob, mono, cells=[k])
+    assert proofs[k].hex() == kat["proofs"][str(k)]
+    coeffs = K.blob_coefficients(K.blob_scalars(blob))
+    q = K.cell_quotient(coeffs, k)
+    a = pow(K.cell_coset_shift(k), 64, r)
+    rem = [(coeffs[j] + a * q[j]) % r for j in range(64)]           # p - q (X^64 - a), degree < 64
+    lhs = K.g1_decompress(K.blob_to_commitment(blob, _lagrange()))
+    shifted = cx.G1.msm(mono[64:64 + len(q)], q)
+    rhs = cx.G1.add(cx.G1.add(shifted, cx.G1.neg(cx.G1.mul(K.g1_decompress(proofs[k]), a))), cx.G1.msm(mono[:64], rem))
+    assert lhs == rhs

@@ -5,6 +5,8 @@ Run in the build container only (reads /root/reference); the GPU box uses the co
   kzg_g1_lagrange.bin   4096 x 48-byte compressed G1 Lagrange points, file order
                         (/root/reference/config/kzg_trusted_setup.txt lines 3..4098)
   kzg_g1_monomial_64.bin first 64 monomial-basis G1 points (lines 4164..) for the cross-check
+  kzg_g1_monomial.bin   all 4096 monomial-basis G1 points (EIP-7594 cell proofs)
+  kzg_cell_kat.json     oracle cell proofs (cells 0, 1, 77, 127) of the first sample blob
   kzg_kat.json          known-answer commitments computed by the oracle (oracle/kzg.py) for the
                         reference's deterministic test blobs (crypto/blobs/testdata.go:101-132) and
                         the first 128 KiB sample blob (crypto/blobs/testdata/blobdata1.txt)
@@ -51,6 +53,13 @@ def main():
         kat["cases"].append({"name": name, "blob_sha256": hashlib.sha256(blob).hexdigest(), "commitment": c.hex()})
         print(name, c.hex())
     json.dump(kat, open(os.path.join(OUT, "kzg_kat.json"), "w"), indent=1)
+    mono_bytes = b"".join(bytes.fromhex(h) for h in mono_hex)
+    open(os.path.join(OUT, "kzg_g1_monomial.bin"), "wb").write(mono_bytes)
+    mono = [kzg.g1_decompress(bytes.fromhex(h)) for h in mono_hex]
+    cells = kzg.compute_cell_proofs(sample, mono, cells=[0, 1, 77, 127])
+    json.dump({"blob": "blobdata1", "mono_sha256": hashlib.sha256(mono_bytes).hexdigest(),
+               "proofs": {str(k): v.hex() for k, v in cells.items()}},
+              open(os.path.join(OUT, "kzg_cell_kat.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
