@@ -202,8 +202,8 @@ def main():
     # ------------------------------------------------------------------ B200 arm
     # NCCL (used only for the barrier / max-over-ranks timing) prints its version banner on stdout at the
     # VERSION debug level, which would precede the one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "NONE"
     import numpy as np
     import torch
     import torch.distributed as dist
