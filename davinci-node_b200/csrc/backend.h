@@ -181,6 +181,10 @@ struct CurveBackend {
                         int nsets, MsmWorkspace& ws, cudaStream_t s, MsmSorted& out) = 0;
   virtual void msm_reduce(int group, const MsmSorted& so, int first_set, int count, const MsmBases* const* bases,
                           void* d_out_xyzz, MsmWorkspace& ws, cudaStream_t s, bool join = true) = 0;
+  // Batched MSM: `batch` scalar vectors of n_per scalars each over ONE base set -> `batch` XYZZ results, with one
+  // sort and one accumulate / reduce pass for all of them (the 128 quotients of the EIP-7594 cell proofs)
+  virtual void msm_batch(int group, const MsmBases& bases, const void* d_scalars, uint64_t n_per, uint32_t batch,
+                         const uint32_t* d_index_map, void* d_out_xyzz, MsmWorkspace& ws, cudaStream_t s) = 0;
   // window width the cost model picks for a table-mode base set of npts points
   virtual int table_window(uint64_t npts) const = 0;
   // precompute T_j[i] = 2^(c j) P_i for a base set (window_bits = 0: cost model)

@@ -304,10 +304,12 @@ void msm_sort_launch(const void* d_scalars, const MsmPlan& pl, const MsmSets& se
   if (pl.pre) B200_CUDA(cudaMemsetAsync(sorted, 0xff, (uint64_t)pl.bwin * pl.stride * 4, s));
   const auto* sc = reinterpret_cast<const typename Fr::El*>(d_scalars);
   const unsigned sblocks = (unsigned)((pl.n + 255) / 256);
-  k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, sets);
+  if (pl.batch_n) k_msm_hist_batch<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, sets);
+  else k_msm_hist<Fr><<<sblocks, 256, 0, s>>>(sc, pl, hist, sets);
   k_msm_scan_sums<<<dim3(nchunks, pl.bwin), kScanThreads, 0, s>>>(hist, pl, chunk_sums);
   k_msm_scan<<<dim3(nchunks, pl.bwin), kScanThreads, 0, s>>>(hist, pl, chunk_sums, off, cur, totals);
-  k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, sets);
+  if (pl.batch_n) k_msm_scatter_batch<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, sets);
+  else k_msm_scatter<Fr><<<sblocks, 256, 0, s>>>(sc, pl, cur, sorted, sets);
   prof_end(tok_sort, s);
   prof_count_launches(4);
   B200_CUDA(cudaGetLastError());
@@ -427,7 +429,7 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   } else {
     k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, t>>>(groups, ngroups, windows);
   }
-  k_msm_horner<F><<<1, 32, 0, t>>>(windows, pl, (Pt*)d_out);
+  k_msm_horner<F><<<1, 128, 0, t>>>(windows, pl, (Pt*)d_out);
   prof_end(tok_sums, t);
   // join: the caller's stream waits for the tail; otherwise the result is ready when ws.e_back fires
   // (ws.wait_tail(other_stream)) and the caller's stream may run ahead with independent bulk work
@@ -508,6 +510,24 @@ struct CurveImpl : CurveBackend {
       msm_set_smem_attrs<G2F>();
       msm_reduce_launch<G2F, 2>(so, pts, d_out, ws, s, join);
     }
+  }
+
+  void msm_batch(int group, const MsmBases& bases, const void* d_scalars, uint64_t n_per, uint32_t batch,
+                 const uint32_t* d_index_map, void* d_out, MsmWorkspace& ws, cudaStream_t s) override {
+    if (bases.group != group) throw std::runtime_error("msm_batch: base tables belong to the other group");
+    if (n_per == 0 || batch == 0 || n_per * batch >= (1ull << 31) || batch > 65535)
+      throw std::runtime_error("msm_batch: bad sizes");
+    MsmPlan pl = make_msm_plan_table(n_per, Fr::BITS, bases.c, bases.npts, (int)batch);
+    pl.n = n_per * batch;
+    pl.batch_n = (uint32_t)n_per;
+    MsmSets sets{};
+    sets.map[0] = d_index_map;
+    sets.npts[0] = bases.npts;
+    MsmPts pts{};
+    pts.p[0] = bases.tables.p;
+    MsmSorted so;
+    msm_sort_launch<Fr>(d_scalars, pl, sets, ws, s, so);
+    reduce_dispatch(group, so, pts, d_out, ws, s, true);
   }
 
   void msm_sort(const void* d_scalars, uint64_t n, const MsmBases* const* bases, const uint32_t* const* maps,

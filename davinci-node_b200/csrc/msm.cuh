@@ -264,6 +264,50 @@ k_msm_scatter(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t*
   }
 }
 
+// Batched mode (pl.batch_n > 0): `bwin` scalar vectors over one shared base set, e.g. the 128 quotient polynomials
+// of the EIP-7594 cell proofs against the monomial SRS.  Vector v feeds bucket array v; plain atomics (the scalars
+// of this mode are quotient coefficients, uniformly distributed).
+template <class Fr>
+__global__ void __launch_bounds__(256)
+k_msm_hist_batch(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ hist, MsmSets sets) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pl.n) return;
+  const uint32_t v = (uint32_t)(i / pl.batch_n), li = (uint32_t)(i % pl.batch_n);
+  if ((sets.map[0] ? sets.map[0][li] : li) == kSkip) return;
+  typename Fr::El s, mont;
+  load16(mont, scalars + i);
+  Fr::from_mont(s, mont);
+  if (Fr::is_zero(s)) return;
+  DigitWalker<Fr::N> dw;
+  uint32_t b;
+  bool neg;
+  for (int w = 0; w < pl.nwin; w++)
+    if (dw.next(s.v, w, pl.c, b, neg)) atomicAdd(&hist[(uint64_t)v * pl.nb + b], 1u);
+}
+
+template <class Fr>
+__global__ void __launch_bounds__(256)
+k_msm_scatter_batch(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ cur,
+                    uint32_t* __restrict__ sorted, MsmSets sets) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pl.n) return;
+  const uint32_t v = (uint32_t)(i / pl.batch_n), li = (uint32_t)(i % pl.batch_n);
+  const uint32_t pidx = sets.map[0] ? sets.map[0][li] : li;
+  if (pidx == kSkip) return;
+  typename Fr::El s, mont;
+  load16(mont, scalars + i);
+  Fr::from_mont(s, mont);
+  if (Fr::is_zero(s)) return;
+  DigitWalker<Fr::N> dw;
+  uint32_t b;
+  bool neg;
+  for (int w = 0; w < pl.nwin; w++) {
+    if (!dw.next(s.v, w, pl.c, b, neg)) continue;
+    uint32_t pos = atomicAdd(&cur[(uint64_t)v * pl.nb + b], 1u);
+    sorted[(uint64_t)v * pl.stride + pos] = (uint32_t)((uint64_t)w * sets.npts[0] + pidx) | (neg ? 0x80000000u : 0u);
+  }
+}
+
 // ------------------------------------------------------------------------------------ accumulate
 struct OvfTask {
   uint32_t bucket;   // global bucket id  a * nb + b   (a = bucket array)
@@ -471,7 +515,7 @@ k_msm_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, const uint32_t
     // else: cannot happen (capacity covers every entry); stay correct anyway by taking the whole bucket
   }
   // DIRECT: pts.p[0] is the pre-reduced affine list (single bucket array), `start` indexes it
-  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[pl.table ? w : 0]) + (DIRECT ? start : 0);
+  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[(pl.table && !pl.batch_n) ? w : 0]) + (DIRECT ? start : 0);
   const uint32_t* idx = DIRECT ? nullptr : sorted + (uint64_t)w * pl.stride + start;
   XYZZ<F> acc;
 #ifdef B200_ACC_LOCKSTEP
@@ -510,7 +554,7 @@ k_msm_ovf_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, MsmPlan pl
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     OvfTask tk = tasks[t];
     uint32_t w = tk.bucket / pl.nb;
-    const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[pl.table ? w : 0]) + (DIRECT ? tk.start : 0);
+    const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[(pl.table && !pl.batch_n) ? w : 0]) + (DIRECT ? tk.start : 0);
     XYZZ<F> acc;
     accumulate_run<F, DIRECT>(acc, points, DIRECT ? nullptr : sorted + (uint64_t)w * pl.stride + tk.start, tk.len);
     store16(partial + t, acc);
@@ -682,10 +726,10 @@ __global__ void k_msm_horner(const XYZZ<F>* __restrict__ windows, MsmPlan pl, XY
   using E = EC<F>;
   if (blockIdx.x) return;
   if (pl.table) {
-    if ((int)threadIdx.x < pl.bwin) {
+    for (int j = threadIdx.x; j < pl.bwin; j += blockDim.x) {
       XYZZ<F> ws;
-      load16_rw(ws, windows + threadIdx.x);
-      store16(out + threadIdx.x, ws);
+      load16_rw(ws, windows + j);
+      store16(out + j, ws);
     }
     return;
   }

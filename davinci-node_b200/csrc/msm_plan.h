@@ -24,6 +24,8 @@ struct MsmPlan {
   int nwin;            // digit windows = ceil((scalar_bits + 1) / c)
   int bwin;            // bucket arrays: nwin (windowed) or the number of base sets (table mode)
   int table;           // 1 = table mode
+  uint32_t batch_n;    // > 0: batched mode - `bwin` scalar vectors of batch_n scalars each share ONE base set (and its
+                       // index map); scalar i belongs to vector i / batch_n and multiplies base (i % batch_n)
   int pre;             // affine pre-reduction levels (msm_pre.cuh): bucket segments are padded to multiples of 2^pre
   uint32_t nb;         // buckets per bucket window = 2^(c-1)
   uint32_t task;       // max points a single thread accumulates for one bucket

@@ -444,11 +444,6 @@ std::unique_ptr<KzgSrsDev> KzgSrsDev::create(const uint8_t* g1_lagrange_compress
 KzgSrsDev::Inst::~Inst() {
   cudaSetDevice(device);
   if (st) cudaStreamDestroy(st);
-  for (auto& l : lane)
-    if (l) cudaStreamDestroy(l);
-  for (auto& e : lane_ev)
-    if (e) cudaEventDestroy(e);
-  if (fork_ev) cudaEventDestroy(fork_ev);
 }
 
 void KzgSrsDev::add_monomial(const uint8_t* g1_monomial_compressed, uint32_t n) {
@@ -476,11 +471,6 @@ void KzgSrsDev::add_monomial(const uint8_t* g1_monomial_compressed, uint32_t n) 
     in->cellq.get((size_t)kCells * npoints * frb);
     in->cell_xyzz.get((size_t)kCells * cb->xyzz_bytes(1));
     in->cell_out.get((size_t)kCells * (g1b + 48));
-    for (int l = 0; l < Inst::kCellLanes; l++) {
-      if (!in->lane[l]) B200_CUDA(cudaStreamCreateWithFlags(&in->lane[l], cudaStreamNonBlocking));
-      if (!in->lane_ev[l]) B200_CUDA(cudaEventCreateWithFlags(&in->lane_ev[l], cudaEventDisableTiming));
-    }
-    if (!in->fork_ev) B200_CUDA(cudaEventCreateWithFlags(&in->fork_ev, cudaEventDisableTiming));
     B200_CUDA(cudaStreamSynchronize(in->st));
     in->have_mono = true;
   }
@@ -499,18 +489,9 @@ void KzgSrsDev::blob_cell_proofs(const uint8_t* blob, uint8_t* proofs, int devic
   // evaluations in bit-reversed order -> coefficients: inverse DIT transform (bit-reversed in, natural out, 1/n)
   cb->ntt(I->dom, I->scalars.p, true, true, false, I->st);
   cb->kzg_cell_quotients(I->scalars.p, I->shifts.p, I->cellq.p, npoints, kCellSize, kCells, I->st);
-  B200_CUDA(cudaEventRecord(I->fork_ev, I->st));
+  // the 128 quotients against the monomial basis: ONE batched MSM (one sort, one accumulate / reduce pass)
   uint8_t* xyzz = (uint8_t*)I->cell_xyzz.p;
-  for (int l = 0; l < Inst::kCellLanes; l++) B200_CUDA(cudaStreamWaitEvent(I->lane[l], I->fork_ev, 0));
-  for (uint32_t k = 0; k < kCells; k++) {
-    const int l = k % Inst::kCellLanes;
-    cb->msm(1, nullptr, (const uint8_t*)I->cellq.p + (size_t)k * npoints * frb, npoints, xyzz + (size_t)k * x1,
-            I->lane_ws[l], I->lane[l], 0, nullptr, nullptr, &I->mono);
-  }
-  for (int l = 0; l < Inst::kCellLanes; l++) {
-    B200_CUDA(cudaEventRecord(I->lane_ev[l], I->lane[l]));
-    B200_CUDA(cudaStreamWaitEvent(I->st, I->lane_ev[l], 0));
-  }
+  cb->msm_batch(1, I->mono, I->cellq.p, npoints, kCells, nullptr, xyzz, I->ws, I->st);
   uint8_t* o = (uint8_t*)I->cell_out.p;
   cb->to_affine(1, xyzz, o, kCells, I->st);
   cb->g1_compress(o, o + (size_t)kCells * g1b, kCells, I->st);

@@ -67,16 +67,11 @@ struct KzgSrsDev {
     MsmBases tables;
     DevBuf brp, blob, scalars, out, err, roots, quot, scratch, zbuf;
     MsmWorkspace ws;
-    // cell proofs: monomial-basis tables, a_k table, 128 quotients, proofs; the 128 MSMs rotate over kCellLanes streams
-    static constexpr int kCellLanes = 8;
+    // cell proofs: monomial-basis tables, a_k table, 128 quotients, proofs
     MsmBases mono;
     bool have_mono = false;
     NttDomain dom;
     DevBuf shifts, cellq, cell_xyzz, cell_out;
-    cudaStream_t lane[kCellLanes] = {};
-    cudaEvent_t lane_ev[kCellLanes] = {};
-    cudaEvent_t fork_ev = nullptr;
-    MsmWorkspace lane_ws[kCellLanes];
     ~Inst();
   };
   CurveBackend* cb = nullptr;
