@@ -413,9 +413,9 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   unsigned ovf_blocks = (unsigned)std::min<uint64_t>((pl.max_ovf + 127) / 128, 148 * 8);
   if (direct) k_msm_ovf_accumulate<F, true><<<ovf_blocks, 128, 0, t>>>(acc_pts, nullptr, pl, tasks, ctr, partial);
   else k_msm_ovf_accumulate<F, false><<<ovf_blocks, 128, 0, t>>>(acc_pts, so.sorted, pl, tasks, ctr, partial);
-  k_msm_ovf_merge_small<F><<<64, 64, 0, t>>>(obuckets, ctr, partial, buckets);
+  k_msm_ovf_merge_small<F><<<148, 64, 0, t>>>(obuckets, ctr, partial, buckets);
   const size_t merge_smem = kOvfMergeThreads * sizeof(Pt);
-  k_msm_ovf_merge_l1<F><<<dim3(32, 64), kOvfMergeThreads, merge_smem, t>>>(obuckets, ctr, partial, mid);
+  k_msm_ovf_merge_l1<F><<<dim3(16, 256), kOvfMergeThreads, merge_smem, t>>>(obuckets, ctr, partial, mid);
   k_msm_ovf_merge_l2<F><<<256, kOvfMergeThreads, merge_smem, t>>>(obuckets, ctr, mid, buckets);
   prof_end(tok_ovf, t);
   size_t red_smem = kReduceThreads * sizeof(Pt);

@@ -42,6 +42,13 @@ def witness_like(rng, n, limbs64, bits, mix="witness"):
     a = rand_canonical(rng, n, limbs64, bits)
     if mix == "uniform":
         return a
+    if mix == "ones":          # every wire 1: each key's whole MSM lands in ONE bucket (maximum skew)
+        a[:] = 0
+        a[:, 0] = 1
+        return a
+    if mix == "zeros":         # nothing but the constant wire (set by the caller)
+        a[:] = 0
+        return a
     u = rng.random(n)
     zero = u < 0.40
     one = (u >= 0.40) & (u < 0.60)

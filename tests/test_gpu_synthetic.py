@@ -54,6 +54,7 @@ def expected_exponents(wl, sol, r, s):
 
 
 @pytest.mark.parametrize("cname,logn,mix", [("bls12_377", 14, "witness"), ("bls12_377", 17, "witness"),
+                                            ("bls12_377", 15, "ones"), ("bn254", 13, "zeros"),
                                             ("bn254", 15, "uniform"), ("bw6_761", 12, "witness"),
                                             ("bls12_377", 22, "witness")])     # BASELINE.json's full size (~40 s)
 def test_structured_key_closed_form(cname, logn, mix):
