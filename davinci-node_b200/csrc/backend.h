@@ -66,7 +66,7 @@ struct DevBuf {
 // blocks of whatever bulk kernel shares the GPU; ordering with the caller's stream is kept by events.
 struct MsmWorkspace {
   DevBuf hist, off, cur, sorted, chunk_sums, buckets, tasks, obuckets, partial, mid, groups, windows, ctr, perm, bins;
-  DevBuf pre_a, pre_b, pre_prefix, off2;   // affine pre-reduction (msm_pre.cuh)
+  DevBuf pre_a, pre_b, pre_prefix, pre_tot, off2;   // affine pre-reduction (msm_pre.cuh)
   cudaStream_t tail = nullptr;
   cudaEvent_t e_fwd = nullptr, e_back = nullptr;
   void ensure_tail() {

@@ -369,11 +369,24 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
       uint32_t per_thread = (uint32_t)std::min<uint64_t>(144, std::max<uint64_t>(8, npairs / (kPreThreads * 148ull * 8)));
       const unsigned blocks = (unsigned)((npairs + (uint64_t)kPreThreads * per_thread - 1) / ((uint64_t)kPreThreads * per_thread));
       El* prefix = (El*)ws.pre_prefix.get((uint64_t)blocks * kPreThreads * per_thread * sizeof(El));
+      // thread totals / their exclusive prefixes / chunk products / scratch of the grid-wide inversion
+      const uint32_t nthreads = blocks * kPreThreads, nchunks = nthreads / kPreInvChunk;
+      El* totals_t = (El*)ws.pre_tot.get(((uint64_t)2 * nthreads + 2 * nchunks + 4) * sizeof(El));
+      El* tpre = totals_t + nthreads;
+      El* cprod = tpre + nthreads;
+      El* cscr = cprod + nchunks;
+      const Affine<F>* src = l == 0 ? (const Affine<F>*)pts.p[0] : in;
       if (l == 0)
-        k_msm_pre_round<F, true><<<blocks, kPreThreads, 0, s>>>((const Affine<F>*)pts.p[0], so.sorted, so.totals, 0,
-                                                                 per_thread, out, prefix);
+        k_msm_pre_fwd<F, true><<<blocks, kPreThreads, 0, s>>>(src, so.sorted, so.totals, 0, per_thread, prefix, totals_t);
       else
-        k_msm_pre_round<F, false><<<blocks, kPreThreads, 0, s>>>(in, nullptr, so.totals, (uint32_t)l, per_thread, out, prefix);
+        k_msm_pre_fwd<F, false><<<blocks, kPreThreads, 0, s>>>(src, nullptr, so.totals, (uint32_t)l, per_thread, prefix, totals_t);
+      k_msm_pre_inv_a<F><<<(nchunks + 63) / 64, 64, 0, s>>>(totals_t, nchunks, tpre, cprod);
+      k_msm_pre_inv_b<F><<<1, kPreThreads, 0, s>>>(cprod, nchunks, cscr);
+      k_msm_pre_inv_c<F><<<(nchunks + 63) / 64, 64, 0, s>>>(totals_t, nchunks, tpre, cprod);
+      if (l == 0)
+        k_msm_pre_bwd<F, true><<<blocks, kPreThreads, 0, s>>>(src, so.sorted, so.totals, 0, per_thread, out, prefix, totals_t);
+      else
+        k_msm_pre_bwd<F, false><<<blocks, kPreThreads, 0, s>>>(src, nullptr, so.totals, (uint32_t)l, per_thread, out, prefix, totals_t);
       in = out;
       out = (out == bufA) ? bufB : bufA;
     }
@@ -383,7 +396,7 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
     k_msm_pre_offsets<<<(unsigned)((total_b + 255) / 256), 256, 0, s>>>(so.off, so.end, total_b, (uint32_t)pl.pre, o2, e2,
                                                                          so.totals, t2, 1);
     prof_end(tok_pre, s);
-    prof_count_launches(pl.pre + 1);
+    prof_count_launches(5 * pl.pre + 1);
     off = o2;
     end = e2;
     totals = t2;

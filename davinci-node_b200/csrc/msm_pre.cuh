@@ -64,42 +64,109 @@ __device__ __forceinline__ int pre_classify(typename F::El& d, const Affine<F>& 
   return 2;
 }
 
-// out[j] = in[2j] + in[2j+1] for j < npairs (npairs = *count_slots >> 1, a device-side value).  Each thread owns
-// `per_thread` pairs (strided by the block size so neighbouring threads touch neighbouring entries); `prefix` is a
-// scratch array of per_thread * gridDim.x * kPreThreads field elements.
+// One level  out[j] = in[2j] + in[2j+1]  (j < npairs = *count_slots >> (shift + 1), a device-side value) runs as
+//   k_msm_pre_fwd      per thread: running product of its `per_thread` denominators (prefix products to scratch),
+//                      thread total to totals[]                                     1 M per addition
+//   k_msm_pre_inv_a/b/c  totals[t] <- 1 / totals[t] for ALL threads of the grid with ONE field inversion
+//                      (Montgomery's trick in two levels; a few hundred thousand elements, microseconds of work)
+//   k_msm_pre_bwd      per thread: peel its denominators off and finish every addition          5 M per addition
+// so no thread ever waits at a barrier for an inversion.  Each thread owns `per_thread` pairs, strided by the block
+// size so neighbouring threads touch neighbouring entries.
+constexpr uint32_t kPreInvChunk = 128;
+
+// x-coordinates decide the common case (both finite, x1 != x2): the forward pass then needs no y at all
 template <class F, bool FROM_TABLE>
-__global__ void __launch_bounds__(kPreThreads)
-k_msm_pre_round(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ count_slots,
-                uint32_t shift, uint32_t per_thread, Affine<F>* __restrict__ out, typename F::El* __restrict__ prefix) {
+__device__ __forceinline__ void pre_denominator(typename F::El& d, const Affine<F>* __restrict__ pts,
+                                                const uint32_t* __restrict__ idx, uint64_t j) {
+  using El = typename F::El;
+  El x1, x2;
+  bool slow = false;
+  if (FROM_TABLE) {
+    const uint32_t e0 = idx[2 * j], e1 = idx[2 * j + 1];
+    if (e0 == kPreSentinel || e1 == kPreSentinel) {
+      slow = true;
+    } else {
+      load16(x1, &pts[e0 & 0x7fffffffu].x);
+      load16(x2, &pts[e1 & 0x7fffffffu].x);
+    }
+  } else {
+    load16(x1, &pts[2 * j].x);
+    load16(x2, &pts[2 * j + 1].x);
+  }
+  if (!slow) {
+    F::sub(d, x2, x1);
+    slow = F::is_zero(d) || F::is_zero(x1) || F::is_zero(x2);
+  }
+  if (slow) {                      // infinity operand, doubling or cancellation: classify on the whole points
+    Affine<F> p, q;
+    pre_load_pair<F, FROM_TABLE>(p, q, pts, idx, j);
+    pre_classify<F>(d, p, q);
+  }
+}
+
+template <class F, bool FROM_TABLE>
+__global__ void __launch_bounds__(kPreThreads, 4)
+k_msm_pre_fwd(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ count_slots,
+              uint32_t shift, uint32_t per_thread, typename F::El* __restrict__ prefix, typename F::El* __restrict__ totals) {
+  using El = typename F::El;
+  const uint64_t npairs = (uint64_t)(*count_slots >> shift) >> 1;
+  const uint64_t block_base = (uint64_t)blockIdx.x * kPreThreads * per_thread;
+  const uint64_t tglobal = (uint64_t)blockIdx.x * kPreThreads + threadIdx.x;
+  El run;
+  F::set_one(run);
+  if (block_base < npairs) {
+    El* my_prefix = prefix + tglobal;                       // element k at my_prefix[k * stride]
+    const uint64_t stride = (uint64_t)gridDim.x * kPreThreads;
+    for (uint32_t k = 0; k < per_thread; k++) {
+      const uint64_t j = block_base + (uint64_t)k * kPreThreads + threadIdx.x;
+      if (j >= npairs) break;
+      El d;
+      pre_denominator<F, FROM_TABLE>(d, pts, idx, j);
+      store16(my_prefix + (uint64_t)k * stride, run);
+      F::mul(run, run, d);
+    }
+  }
+  store16(totals + tglobal, run);
+}
+
+// ---- totals[i] <- 1 / totals[i] for i < m  (m a multiple of kPreInvChunk; every element non-zero)
+// a: thread u: exclusive prefix products of its chunk -> tpre, chunk product -> cprod[u]
+template <class F>
+__global__ void __launch_bounds__(64) k_msm_pre_inv_a(const typename F::El* __restrict__ totals, uint32_t nchunks,
+                                                      typename F::El* __restrict__ tpre, typename F::El* __restrict__ cprod) {
+  using El = typename F::El;
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nchunks) return;
+  El run;
+  F::set_one(run);
+  for (uint32_t i = 0; i < kPreInvChunk; i++) {
+    const uint64_t e = (uint64_t)u * kPreInvChunk + i;
+    El t;
+    load16_rw(t, totals + e);
+    store16(tpre + e, run);
+    F::mul(run, run, t);
+  }
+  store16(cprod + u, run);
+}
+
+// b: ONE block: cprod[u] <- 1 / cprod[u] for u < nchunks, with a single inversion
+template <class F>
+__global__ void __launch_bounds__(kPreThreads) k_msm_pre_inv_b(typename F::El* __restrict__ cprod, uint32_t nchunks,
+                                                                typename F::El* __restrict__ scratch) {
   using El = typename F::El;
   __shared__ El sm_pre[kPreThreads];
   __shared__ El sm_suf[kPreThreads];
   __shared__ El sm_inv;
-  const uint64_t npairs = (uint64_t)(*count_slots >> shift) >> 1;
-  const uint64_t block_base = (uint64_t)blockIdx.x * kPreThreads * per_thread;
-  if (block_base >= npairs) return;
-  const uint64_t tglobal = (uint64_t)blockIdx.x * kPreThreads + threadIdx.x;
-  El* my_prefix = prefix + tglobal;                       // element k at my_prefix[k * stride]
-  const uint64_t stride = (uint64_t)gridDim.x * kPreThreads;
-
-  // ---- forward: running product of the denominators
+  const uint32_t per = (nchunks + kPreThreads - 1) / kPreThreads;
+  const uint32_t lo = threadIdx.x * per, hi = lo + per < nchunks ? lo + per : nchunks;
   El run;
   F::set_one(run);
-  for (uint32_t k = 0; k < per_thread; k++) {
-    const uint64_t j = block_base + (uint64_t)k * kPreThreads + threadIdx.x;
-    El d;
-    if (j < npairs) {
-      Affine<F> p, q;
-      pre_load_pair<F, FROM_TABLE>(p, q, pts, idx, j);
-      pre_classify<F>(d, p, q);
-    } else {
-      F::set_one(d);
-    }
-    store16(my_prefix + (uint64_t)k * stride, run);
-    F::mul(run, run, d);
+  for (uint32_t u = lo; u < hi; u++) {
+    El t;
+    load16_rw(t, cprod + u);
+    store16(scratch + u, run);                            // exclusive prefix inside this thread's range
+    F::mul(run, run, t);
   }
-
-  // ---- one inversion per block: inclusive prefix / suffix products of the thread totals (Hillis-Steele)
   sm_pre[threadIdx.x] = run;
   sm_suf[threadIdx.x] = run;
   __syncthreads();
@@ -115,16 +182,69 @@ k_msm_pre_round(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ 
   }
   if (threadIdx.x == 0) F::inv(sm_inv, sm_pre[kPreThreads - 1]);
   __syncthreads();
-  El rinv = sm_inv;                                        // 1 / (product of this thread's denominators)
+  El rinv = sm_inv;
   if (threadIdx.x > 0) F::mul(rinv, rinv, sm_pre[threadIdx.x - 1]);
   if (threadIdx.x + 1 < kPreThreads) F::mul(rinv, rinv, sm_suf[threadIdx.x + 1]);
+  for (uint32_t u = hi; u > lo; u--) {
+    El t, pre, o;
+    load16_rw(t, cprod + (u - 1));
+    load16_rw(pre, scratch + (u - 1));
+    F::mul(o, rinv, pre);
+    F::mul(rinv, rinv, t);
+    store16(cprod + (u - 1), o);
+  }
+}
 
-  // ---- backward: peel the denominators off, finish every addition
-  for (int k = (int)per_thread - 1; k >= 0; k--) {
+// c: thread u: back-substitution inside its chunk
+template <class F>
+__global__ void __launch_bounds__(64) k_msm_pre_inv_c(typename F::El* __restrict__ totals, uint32_t nchunks,
+                                                      const typename F::El* __restrict__ tpre,
+                                                      const typename F::El* __restrict__ cinv) {
+  using El = typename F::El;
+  const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= nchunks) return;
+  El rinv;
+  load16_rw(rinv, cinv + u);
+  for (int i = (int)kPreInvChunk - 1; i >= 0; i--) {
+    const uint64_t e = (uint64_t)u * kPreInvChunk + i;
+    El t, pre, o;
+    load16_rw(t, totals + e);
+    load16_rw(pre, tpre + e);
+    F::mul(o, rinv, pre);
+    F::mul(rinv, rinv, t);
+    store16(totals + e, o);
+  }
+}
+
+template <class F, bool FROM_TABLE>
+__global__ void __launch_bounds__(kPreThreads, 3)
+k_msm_pre_bwd(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ count_slots,
+              uint32_t shift, uint32_t per_thread, Affine<F>* __restrict__ out, const typename F::El* __restrict__ prefix,
+              const typename F::El* __restrict__ totals) {
+  using El = typename F::El;
+  const uint64_t npairs = (uint64_t)(*count_slots >> shift) >> 1;
+  const uint64_t block_base = (uint64_t)blockIdx.x * kPreThreads * per_thread;
+  if (block_base >= npairs) return;
+  const uint64_t tglobal = (uint64_t)blockIdx.x * kPreThreads + threadIdx.x;
+  const El* my_prefix = prefix + tglobal;
+  const uint64_t stride = (uint64_t)gridDim.x * kPreThreads;
+  // this thread's pairs are k = 0 .. kmax-1
+  int kmax = 0;
+  if (block_base + threadIdx.x < npairs) {
+    const uint64_t span = npairs - block_base - threadIdx.x;            // >= 1
+    const uint64_t cnt = (span + kPreThreads - 1) / kPreThreads;
+    kmax = (int)(cnt < per_thread ? cnt : per_thread);
+  }
+  if (kmax == 0) return;
+  El rinv;
+  load16_rw(rinv, totals + tglobal);                                     // 1 / (product of this thread's denominators)
+  // software pipeline: the operands of the next (lower) pair are in flight while this addition is finished
+  Affine<F> np, nq;
+  pre_load_pair<F, FROM_TABLE>(np, nq, pts, idx, block_base + (uint64_t)(kmax - 1) * kPreThreads + threadIdx.x);
+  for (int k = kmax - 1; k >= 0; k--) {
     const uint64_t j = block_base + (uint64_t)k * kPreThreads + threadIdx.x;
-    if (j >= npairs) continue;                             // its denominator was 1
-    Affine<F> p, q, r;
-    pre_load_pair<F, FROM_TABLE>(p, q, pts, idx, j);
+    Affine<F> p = np, q = nq, r;
+    if (k > 0) pre_load_pair<F, FROM_TABLE>(np, nq, pts, idx, j - kPreThreads);
     El d, pre, dinv;
     const int kind = pre_classify<F>(d, p, q);
     load16_rw(pre, my_prefix + (uint64_t)k * stride);
