@@ -82,6 +82,8 @@ _PROTOS = {
     "b200_kzg_srs_add_monomial": (_i, [_u64, _vp, _u32]),
     "b200_blob_cell_proofs": (_i, [_u64, _vp, _vp, _i]),
     "b200_init": (_i, [_u32]),
+    "b200_host_register": (_i, [_vp, _u64]),
+    "b200_host_unregister": (_i, [_vp]),
     "b200_device_count": (_i, []),
     "b200_last_error": (C.c_char_p, []),
     "b200_version": (C.c_char_p, []),

@@ -195,6 +195,21 @@ int b200_init(uint32_t device_mask) {
   });
 }
 
+// Page-lock caller memory (a Go slice that lives across proofs: solver output buffers) so that b200_prove's
+// host-to-device copies run at full PCIe rate and asynchronously; pageable memory is staged by the driver.
+int b200_host_register(void* ptr, uint64_t bytes) {
+  return guarded([&] {
+    if (!ptr || !bytes) throw std::runtime_error("null argument");
+    B200_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  });
+}
+int b200_host_unregister(void* ptr) {
+  return guarded([&] {
+    if (!ptr) throw std::runtime_error("null argument");
+    B200_CUDA(cudaHostUnregister(ptr));
+  });
+}
+
 uint64_t b200_fr_bytes(int c) { return backend_by_id(c) ? backend_by_id(c)->fr_bytes() : 0; }
 uint64_t b200_fp_bytes(int c) { return backend_by_id(c) ? backend_by_id(c)->fp_bytes() : 0; }
 uint64_t b200_affine_bytes(int c, int g) { return backend_by_id(c) ? backend_by_id(c)->affine_bytes(g) : 0; }

@@ -42,6 +42,13 @@ B200_API int b200_device_count(void);
 B200_API const char* b200_last_error(void);
 B200_API const char* b200_version(void);
 
+/* Page-lock / unlock caller memory (cudaHostRegister).  Go heap memory is pageable: copies from it are staged by
+ * the driver at a fraction of the PCIe rate (537 MB of witness + constraint vectors per voteverifier proof).  A shim
+ * that keeps its solver output buffers across proofs registers them once; b200_prove accepts either kind.
+ * Replaces nothing in the reference (gnark's CPU prover never leaves host memory). */
+B200_API int b200_host_register(void* ptr, uint64_t bytes);
+B200_API int b200_host_unregister(void* ptr);
+
 /* element / point sizes in bytes for a curve (group: 1 = G1, 2 = G2) */
 B200_API uint64_t b200_fr_bytes(int curve);
 B200_API uint64_t b200_fp_bytes(int curve);

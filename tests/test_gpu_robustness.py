@@ -90,3 +90,37 @@ def test_pageable_and_pinned_inputs_agree(wl):
         capi.check(capi.lib.b200_prove(wl.handle, C.byref(pin), C.byref(pout), 0))
         outs.append(out.numpy().copy())
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_host_register_roundtrip():
+    """b200_host_register page-locks caller memory (what a Go shim does with its long-lived solver buffers); a proof
+    from registered numpy buffers equals the proof from pageable ones."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from davinci_node_b200 import capi, prover, synthetic
+    capi.init()
+    wl = synthetic.SyntheticWorkload("bn254", 12, seed=5)
+    h = wl.register()
+    try:
+        sol = wl.solution(seed=3, pinned=False)
+        L = wl.L
+        r, s = 123456789 % L.r, 987654321 % L.r
+        outs = []
+        for register in (False, True):
+            bufs = {k: np.array(sol[k].numpy(), copy=True) for k in ("W", "a", "b", "c")}
+            if register:
+                for v in bufs.values():
+                    capi.check(capi.lib.b200_host_register(v.ctypes.data, v.nbytes))
+            fake = dict(sol)
+            fake.update({k: torch.from_numpy(v) for k, v in bufs.items()})
+            pin, pout, out, keep = wl.prove_args(fake, r, s, on_device=False)
+            capi.check(capi.lib.b200_prove(h, C.byref(pin), C.byref(pout), 0))
+            outs.append(bytes(out.numpy()))
+            if register:
+                for v in bufs.values():
+                    capi.check(capi.lib.b200_host_unregister(v.ctypes.data))
+        assert outs[0] == outs[1]
+        assert capi.lib.b200_host_register(None, 16) != 0
+    finally:
+        prover.release_proving_key(wl.pk)
