@@ -212,7 +212,8 @@ B200_API int b200_profile_enable(int on);
 B200_API int b200_profile_collect(double ms_out[5], uint64_t count_out[5]);
 /* every instrumented phase recorded since b200_profile_enable(1), 4 doubles per record: [tag, stream ordinal,
  * start ms, end ms].  Further tags: 5 digit/sort, 6 bucket schedule, 7 oversized buckets, 8 bucket reduction,
- * 9 window sums, 10 input copies, 11 proof assembly.  Synchronises the device; does not clear. */
+ * 9 window sums, 10 input copies, 11 proof assembly, 12 affine pre-reduction (opt-in).  Synchronises the device;
+ * does not clear. */
 B200_API int b200_profile_timeline(double* out, uint64_t cap_records, uint64_t* n_out);
 
 /* ---- debug / parity entry points (device pointers; element-wise over n items) ---------------
