@@ -1,13 +1,17 @@
 // Signed-digit Pippenger multi-scalar multiplication for sm_100a.
 //
-//   digits/histogram -> per-window exclusive scan -> counting-sort scatter (point index | sign)
-//   -> bucket accumulation (one thread per bucket, 128-bit gathered affine loads, XYZZ mixed adds;
-//      oversized buckets are split into fixed-size tasks and merged by a block reduction)
-//   -> bucket reduction (running sums over groups of buckets, [base]*sum fix-up per group)
-//   -> per-window block reduction -> Horner combine of the windows.
+//   stage 1 (sort)    digits/histogram -> multi-block exclusive scan -> counting-sort scatter of (table index | sign)
+//                     entries.  Table mode: one pass feeds up to 4 base sets that share the scalar vector (the A / B / K
+//                     keys of a Groth16 proof), or - batched mode - many scalar vectors over one base set.
+//   stage 2 (reduce)  [optional affine pre-reduction, msm_pre.cuh] -> size-sorted bucket schedule
+//                     -> bucket accumulation (one thread per bucket, 128-bit gathered affine loads, XYZZ mixed adds,
+//                        lock-step iterations; oversized buckets are cut into 32-point tasks)
+//                     -> tail on a high-priority stream: overflow partial sums (small buckets: one thread; big ones:
+//                        two-level block tree), bucket reduction (running sums over groups of buckets, [base]*sum
+//                        fix-up per group), per-array block reductions, Horner (windowed mode only).
 //
-// Everything runs on one stream with no host synchronisation; scalars are consumed in
-// gnark-crypto's Montgomery form (converted in-register), points in gnark's affine layout.
+// No host synchronisation anywhere; scalars are consumed in gnark-crypto's Montgomery form (converted in-register),
+// points in gnark's affine layout.
 //
 // Replaces `G1Affine.MultiExp` / `G2Affine.MultiExp` (gnark-crypto, go.mod:16) as called for the
 // Ar / Bs1 / Bs / Krs / Krs2 and Pedersen commitments of groth16.Prove

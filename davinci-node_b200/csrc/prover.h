@@ -11,8 +11,7 @@
 namespace b200 {
 
 // Workspace + streams for ONE proof in flight.  A key instance owns several slots so that the
-// latency-bound tails of one proof (Horner, bucket reduction, assembly, copies) overlap the
-// accumulation kernels of the next one.
+// input copies, MSM tails and assembly of one proof overlap the bulk kernels of the next one.
 struct PkSlot {
   int device;
   std::mutex mu;
