@@ -101,4 +101,6 @@ def main():
 
 
 if __name__ == "__main__":
+    import signal
+    signal.signal(signal.SIGPIPE, signal.SIG_DFL)      # `| head` must not end in a traceback
     main()
