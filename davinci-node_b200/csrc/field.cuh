@@ -64,6 +64,7 @@ struct FpT {
   using Params = P;
   static constexpr int N = P::N;
   static constexpr int LIMBS = P::N;
+  static constexpr int BASE_N = P::N;      // limbs of the prime field the arithmetic bottoms out in
   static constexpr int BITS = P::BITS;
   using El = Limbs<N>;
 
@@ -151,6 +152,7 @@ struct Fp2T {
   using Base = FpT<P>;
   using BEl = typename Base::El;
   static constexpr int LIMBS = 2 * P::N;
+  static constexpr int BASE_N = P::N;
   struct alignas(16) El {
     BEl c0, c1;
   };

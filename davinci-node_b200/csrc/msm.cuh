@@ -380,10 +380,13 @@ __device__ __forceinline__ void accumulate_run(XYZZ<F>& acc, const Affine<F>* __
 // iteration, so the (64 KB, larger than the instruction cache) loop body is streamed once per SM and
 // iteration instead of once per warp.  Buckets of a block have (almost) equal sizes thanks to the
 // size-sorted schedule, so the padding iterations are few.
+template <class F>
+struct AccCfg;
 template <class F, bool DIRECT>
 __device__ __forceinline__ void accumulate_run_lockstep(XYZZ<F>& acc, const Affine<F>* __restrict__ points,
                                                         const uint32_t* __restrict__ idx, uint32_t len) {
   using E = EC<F>;
+  constexpr bool kPrefetch = AccCfg<F>::kPrefetch;
   __shared__ uint32_t s_trips;
   E::set_inf(acc);
   if (threadIdx.x == 0) s_trips = 0;
@@ -393,13 +396,14 @@ __device__ __forceinline__ void accumulate_run_lockstep(XYZZ<F>& acc, const Affi
   const uint32_t trips = s_trips;
   uint32_t e = 0;
   Affine<F> nxt;
-  if (len) accumulate_fetch<F, DIRECT>(nxt, e, points, idx, 0);
+  if (kPrefetch && len) accumulate_fetch<F, DIRECT>(nxt, e, points, idx, 0);
   for (uint32_t k = 0; k < trips; k++) {
     __syncthreads();
     if (k < len) {
+      if (!kPrefetch) accumulate_fetch<F, DIRECT>(nxt, e, points, idx, k);
       Affine<F> cur = nxt;
       bool neg = e >> 31;
-      if (k + 1 < len) accumulate_fetch<F, DIRECT>(nxt, e, points, idx, k + 1);
+      if (kPrefetch && k + 1 < len) accumulate_fetch<F, DIRECT>(nxt, e, points, idx, k + 1);
       if (neg) E::neg(cur);
       E::madd(acc, cur);
     }
@@ -480,7 +484,11 @@ k_msm_size_scatter(const uint32_t* __restrict__ off, const uint32_t* __restrict_
 #define B200_ACC_MIN_BLOCKS 3
 #endif
 #ifndef B200_ACC_MIN_BLOCKS_BIG
-#define B200_ACC_MIN_BLOCKS_BIG 3   // coordinate fields of >= 96 bytes (Fp2 over 377/381-bit primes, BW6-761 Fp)
+#define B200_ACC_MIN_BLOCKS_BIG 3   // Fp2 over a 12-limb prime field (G2 of BLS12-377 / BLS12-381): measured better than 2
+#endif
+#ifndef B200_ACC_MIN_BLOCKS_WIDE
+#define B200_ACC_MIN_BLOCKS_WIDE 2  // 24-limb prime field (BW6-761): one 1176-MAC product needs ~100 registers of its own;
+                                    // 255 registers at 2 blocks per SM: 47.8 -> 38.5 ms for a 2^20 MSM
 #endif
 #ifndef B200_ACC_MIN_BLOCKS_SMALL
 #define B200_ACC_MIN_BLOCKS_SMALL 4   // 32-byte coordinate fields (BN254 Fp): 126 registers, measured -5% vs 3 blocks
@@ -490,9 +498,12 @@ k_msm_size_scatter(const uint32_t* __restrict__ off, const uint32_t* __restrict_
 #endif
 template <class F>
 struct AccCfg {
-  static constexpr int kMinBlocks = sizeof(typename F::El) >= 96   ? B200_ACC_MIN_BLOCKS_BIG
-                                    : sizeof(typename F::El) <= 32 ? B200_ACC_MIN_BLOCKS_SMALL
-                                                                   : B200_ACC_MIN_BLOCKS;
+  static constexpr int kMinBlocks = F::BASE_N >= 24                 ? B200_ACC_MIN_BLOCKS_WIDE
+                                    : sizeof(typename F::El) >= 96  ? B200_ACC_MIN_BLOCKS_BIG
+                                    : sizeof(typename F::El) <= 32  ? B200_ACC_MIN_BLOCKS_SMALL
+                                                                    : B200_ACC_MIN_BLOCKS;
+  // one-point prefetch: not for Fp2 points (48 more registers in a kernel that already spills; measured +1.5% without)
+  static constexpr bool kPrefetch = !(sizeof(typename F::El) >= 96 && F::BASE_N < 24);
 };
 template <class F, bool DIRECT>
 __global__ void __launch_bounds__(B200_ACC_THREADS, AccCfg<F>::kMinBlocks)
