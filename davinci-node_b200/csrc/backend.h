@@ -199,7 +199,9 @@ struct CurveBackend {
   virtual void scale_vec(void* d_x, const void* d_c, uint64_t n, cudaStream_t s) = 0;
   // writes r, s, 1, -r*s (Montgomery) to d_out[0..4) from canonical-or-Montgomery inputs already on device
   virtual void prep_rs(const void* d_r, const void* d_s, void* d_out4, cudaStream_t s) = 0;
-  virtual void assemble(const AssembleArgs& a, cudaStream_t s) = 0;
+  // phases: 1 = the two scalar multiplications s*Ar, r*Bs1 (need only the wire-indexed G1 MSMs), 2 = sums and affine
+  // normalisation (needs everything), 3 = both
+  virtual void assemble(const AssembleArgs& a, cudaStream_t s, int phases = 3) = 0;
   // --- EIP-4844 helpers (BLS12-381 only; other curves throw)
   virtual void g1_decompress(const void* d_bytes, void* d_affine, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;
   virtual void g1_compress(const void* d_affine, void* d_bytes, uint32_t n, cudaStream_t s) = 0;

@@ -794,14 +794,19 @@ struct CurveImpl : CurveBackend {
     B200_CUDA(cudaGetLastError());
   }
 
-  void assemble(const AssembleArgs& a, cudaStream_t s) override {
+  void assemble(const AssembleArgs& a, cudaStream_t s, int phases) override {
     using P1 = XYZZ<G1F>;
-    prof_count_launches(2);
-    k_assemble_mul<G1F, Fr><<<2, 1, 0, s>>>((const P1*)a.ar_msm, (const P1*)a.bs1_msm, (const FrEl*)a.rs, (P1*)a.tmp);
-    k_assemble_out<G1F, G2F><<<4, 1, 0, s>>>((const P1*)a.ar_msm, (const XYZZ<G2F>*)a.bs2_msm, (const P1*)a.k_msm,
-                                              (const P1*)a.z_msm, (const P1*)a.pok_msm, (const P1*)a.tmp,
-                                              (Affine<G1F>*)a.out_ar, (Affine<G2F>*)a.out_bs,
-                                              (Affine<G1F>*)a.out_krs, (Affine<G1F>*)a.out_pok);
+    if (phases & 1) {
+      prof_count_launches(1);
+      k_assemble_mul<G1F, Fr><<<2, 1, 0, s>>>((const P1*)a.ar_msm, (const P1*)a.bs1_msm, (const FrEl*)a.rs, (P1*)a.tmp);
+    }
+    if (phases & 2) {
+      prof_count_launches(1);
+      k_assemble_out<G1F, G2F><<<4, 1, 0, s>>>((const P1*)a.ar_msm, (const XYZZ<G2F>*)a.bs2_msm, (const P1*)a.k_msm,
+                                                (const P1*)a.z_msm, (const P1*)a.pok_msm, (const P1*)a.tmp,
+                                                (Affine<G1F>*)a.out_ar, (Affine<G2F>*)a.out_bs,
+                                                (Affine<G1F>*)a.out_krs, (Affine<G1F>*)a.out_pok);
+    }
     B200_CUDA(cudaGetLastError());
   }
 
