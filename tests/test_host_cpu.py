@@ -84,3 +84,28 @@ def test_solver_mirror_and_witness_errors():
     assert Layout(1).dec_fr(sol.A) == a and Layout(1).dec_fr(sol.C) == c
     with pytest.raises(ValueError):
         ccs.solve(T.Witness(1, W[1:2], []))
+
+
+def test_bench_reference_arm_contract_and_no_cpu_fallback():
+    """bench.py --impl reference (the CPU restatement timed on the host cores) prints ONE JSON line with the
+    contract's keys; the B200 arm refuses to run without a GPU instead of falling back to the CPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--logn", "12", "--cpu-logn", "10"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1", "--logn", "10"],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
