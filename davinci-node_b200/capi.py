@@ -61,6 +61,8 @@ _PROTOS = {
     "b200_compute_h_dev": (_i, [_u64, _vp, _vp, _vp, _vp]),
     "b200_pk_register": (_i, [C.POINTER(PkDesc), C.POINTER(_u64)]),
     "b200_pk_release": (_i, [_u64]),
+    "b200_set_pk_table_budget": (_i, [_u64]),
+    "b200_pk_info": (_i, [_u64, C.POINTER(_u64)]),
     "b200_commit": (_i, [_u64, _u32, Slice, _vp, _i]),
     "b200_prove": (_i, [_u64, C.POINTER(ProveIn), C.POINTER(ProofOut), _i]),
     "b200_prove_dev": (_i, [_u64, C.POINTER(ProveIn), C.POINTER(ProofOut), _i]),
@@ -125,6 +127,12 @@ def init(device_mask=0):
 def init_once():
     if not _inited:
         init(int(os.environ.get("B200_DEVICE_MASK", "0"), 0))
+
+
+def pk_info(handle):
+    out = (_u64 * 6)()
+    check(lib.b200_pk_info(handle, out))
+    return dict(table_stride=out[0], table_bytes=out[1], slots=out[2], wire_window=out[3], z_window=out[4], gpus=out[5])
 
 
 def msm_plan(curve, n, window_bits=0):

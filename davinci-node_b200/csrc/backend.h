@@ -100,9 +100,11 @@ struct MsmWorkspace {
 
 // A base-point set with its precomputed window multiples resident in HBM ("table mode", msm_plan.h)
 struct MsmBases {
-  DevBuf tables;      // nwin tables of npts affine points: T_j[i] = 2^(c j) P_i
+  DevBuf tables;      // ntab tables of npts affine points: T_q[i] = 2^(c tstride q) P_i
   uint64_t npts = 0;
   int c = 0, nwin = 0, group = 1;
+  int tstride = 1;    // table stride (msm_plan.h): 1 = a table per digit window
+  int ntab = 0;       // ceil(nwin / tstride)
 };
 
 }  // namespace b200
@@ -143,7 +145,7 @@ struct AssembleArgs {
   const void* ar_msm;     // sum w_i A_i + alpha + r delta      (G1)
   const void* bs1_msm;    // sum w_i B_i + beta + s delta       (G1)
   const void* bs2_msm;    // same in G2
-  const void* k_msm;      // sum w_i K_i - r s delta            (G1)
+  const void* k_msm;      // sum w_i K_i - r s delta            (G1; written by phase 4)
   const void* z_msm;      // sum h_i Z_i                        (G1)
   const void* pok_msm;    // may be null                        (G1)
   const void* rs;         // 4 Fr elements (Montgomery): r, s, 1, -r s
@@ -186,10 +188,10 @@ struct CurveBackend {
   virtual void msm_batch(int group, const MsmBases& bases, const void* d_scalars, uint64_t n_per, uint32_t batch,
                          const uint32_t* d_index_map, void* d_out_xyzz, MsmWorkspace& ws, cudaStream_t s) = 0;
   // window width the cost model picks for a table-mode base set of npts points
-  virtual int table_window(uint64_t npts) const = 0;
-  // precompute T_j[i] = 2^(c j) P_i for a base set (window_bits = 0: cost model)
+  virtual int table_window(uint64_t npts, int tstride = 1) const = 0;
+  // precompute T_q[i] = 2^(c tstride q) P_i for a base set (window_bits = 0: cost model)
   virtual void build_tables(MsmBases& b, int group, const void* d_points, uint64_t npts, int window_bits,
-                            cudaStream_t s) = 0;
+                            cudaStream_t s, int tstride = 1) = 0;
   // --- NTT / quotient
   virtual void domain_init(NttDomain& d, int logn, const void* d_omega, const void* d_g, cudaStream_t s) = 0;
   // gnark fft.Domain semantics: inverse ? FFTInverse : FFT ; dit ? DIT (bit-reversed in) : DIF ; coset
@@ -199,8 +201,8 @@ struct CurveBackend {
   virtual void scale_vec(void* d_x, const void* d_c, uint64_t n, cudaStream_t s) = 0;
   // writes r, s, 1, -r*s (Montgomery) to d_out[0..4) from canonical-or-Montgomery inputs already on device
   virtual void prep_rs(const void* d_r, const void* d_s, void* d_out4, cudaStream_t s) = 0;
-  // phases: 1 = the two scalar multiplications s*Ar, r*Bs1 (need only the wire-indexed G1 MSMs), 2 = sums and affine
-  // normalisation (needs everything), 3 = both
+  // phases (bit mask): 1 = the two scalar multiplications tmp = {s*Ar, r*Bs1} (need only the wire-indexed G1 MSMs),
+  // 2 = sums and affine normalisation (needs everything), 4 = k_msm += tmp[0] + tmp[1] in place (range-split slices)
   virtual void assemble(const AssembleArgs& a, cudaStream_t s, int phases = 3) = 0;
   // --- EIP-4844 helpers (BLS12-381 only; other curves throw)
   virtual void g1_decompress(const void* d_bytes, void* d_affine, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;

@@ -354,6 +354,25 @@ int b200_pk_release(uint64_t h) {
   });
 }
 
+int b200_set_pk_table_budget(uint64_t bytes) {
+  set_pk_table_budget(bytes);
+  return 0;
+}
+
+int b200_pk_info(uint64_t h, uint64_t out[6]) {
+  return guarded([&] {
+    if (!out) throw std::runtime_error("null argument");
+    auto pk = find_pk(h);
+    PkInstance& I = *pk->inst.at(0);
+    out[0] = (uint64_t)I.tA.tstride;   // as clamped to the number of digit windows
+    out[1] = I.table_bytes;
+    out[2] = I.slots.size();
+    out[3] = (uint64_t)I.tA.c;
+    out[4] = (uint64_t)I.tZ.c;
+    out[5] = pk->inst.size();
+  });
+}
+
 int b200_commit(uint64_t h, uint32_t i, b200_slice values, void* out, int device) {
   return guarded([&] {
     if (!out) throw std::runtime_error("null output");
@@ -386,13 +405,16 @@ int b200_prove_partial_dev(uint64_t h, const b200_prove_in* in, void* d_partials
 int b200_assemble_dev(int curve_id, const void* d_partials, uint32_t nparts, const void* d_r, const void* d_s,
                       int have_pok, void* d_out, void* stream) {
   return guarded([&] {
-    if (!d_partials || !nparts || !d_r || !d_s || !d_out) throw std::runtime_error("null argument");
+    if (!d_partials || !nparts || !d_out) throw std::runtime_error("null argument");
     CurveBackend& cb = curve(curve_id);
     cudaStream_t s = (cudaStream_t)stream;
     const size_t x1 = cb.xyzz_bytes(1), x2 = cb.xyzz_bytes(2), g1b = cb.affine_bytes(1), frb = cb.fr_bytes();
-    ScopedDev sums(5 * x1 + x2), rs(4 * frb), tmp(2 * x1);
+    (void)d_r;   // every slice already folded s*Ar_g + r*Bs1_g into its K partial (b200_prove_partial_dev)
+    (void)d_s;
+    (void)frb;
+    ScopedDev sums(5 * x1 + x2), tmp(2 * x1);
     cb.sum_sets(d_partials, nparts, sums.p, s);
-    cb.prep_rs(d_r, d_s, rs.p, s);
+    B200_CUDA(cudaMemsetAsync(tmp.p, 0, 2 * x1, s));   // two points at infinity
     uint8_t* sm = (uint8_t*)sums.p;
     uint8_t* o = (uint8_t*)d_out;
     AssembleArgs aa{};
@@ -402,13 +424,13 @@ int b200_assemble_dev(int curve_id, const void* d_partials, uint32_t nparts, con
     aa.z_msm = sm + 3 * x1;
     aa.pok_msm = have_pok ? sm + 4 * x1 : nullptr;
     aa.bs2_msm = sm + 5 * x1;
-    aa.rs = rs.p;
+    aa.rs = nullptr;
     aa.tmp = tmp.p;
     aa.out_ar = o;
     aa.out_krs = o + g1b;
     aa.out_pok = o + 2 * g1b;
     aa.out_bs = o + 3 * g1b;
-    cb.assemble(aa, s);
+    cb.assemble(aa, s, 2);
     B200_CUDA(cudaStreamSynchronize(s));   // scratch is scoped to this call
   });
 }

@@ -164,8 +164,18 @@ __global__ void k_assemble_mul(const XYZZ<F>* ar, const XYZZ<F>* bs1, const type
     Fr::from_mont(k, rs[0]);
     p = *bs1;
   }
-  EC<F>::template mul_scalar<Fr::N>(r, p, k.v);
+  EC<F>::template mul_scalar_w4<Fr::N>(r, p, k.v);
   tmp[blockIdx.x] = r;
+}
+
+// k += tmp[0] + tmp[1]: a range-split slice folds s*Ar_g + r*Bs1_g into its K partial sum before the gather
+template <class F>
+__global__ void k_assemble_fold(XYZZ<F>* k, const XYZZ<F>* tmp) {
+  if (threadIdx.x || blockIdx.x) return;
+  XYZZ<F> acc = *k;
+  EC<F>::add(acc, tmp[0]);
+  EC<F>::add(acc, tmp[1]);
+  *k = acc;
 }
 
 // block 0: Krs = K + Z + s*Ar + r*Bs1 -> affine ; 1: Ar -> affine ; 2: Bs (G2) -> affine ; 3: Pok -> affine
@@ -338,8 +348,25 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   // window sums run in one or two slice-sum levels
   const uint32_t kSlices = 64;
   const bool two_level = ngroups >= 4 * kSlices;
-  Pt* groups = (Pt*)ws.groups.get(((uint64_t)pl.bwin * ngroups + (uint64_t)pl.bwin * kSlices) * sizeof(Pt));
-  Pt* mids = groups + (uint64_t)pl.bwin * ngroups;
+  // hierarchical running sums (msm.cuh): level 0 emits acc / run per group of pl.group buckets, the levels above
+  // reduce the run values in groups of 16 until one group is left
+  WsumLevels lv{};
+  uint64_t upper_pts = 0;
+  {
+    uint32_t cnt = ngroups;
+    while (cnt > 1) {
+      if (lv.n >= kWsumMaxLevels) throw std::runtime_error("msm: bucket reduction depth");
+      cnt = (cnt + (1u << kWsumUpperLogG) - 1) >> kWsumUpperLogG;
+      lv.acc_off[lv.n] = (uint32_t)upper_pts;
+      lv.cnt[lv.n] = cnt;
+      upper_pts += 2ull * pl.bwin * cnt;   // acc | run of the level
+      lv.n++;
+    }
+  }
+  Pt* groups = (Pt*)ws.groups.get(((uint64_t)2 * pl.bwin * ngroups + (uint64_t)pl.bwin * kSlices + upper_pts) * sizeof(Pt));
+  Pt* runs0 = groups + (uint64_t)pl.bwin * ngroups;
+  Pt* mids = runs0 + (uint64_t)pl.bwin * ngroups;
+  Pt* upper = mids + (uint64_t)pl.bwin * kSlices;
   Pt* windows = (Pt*)ws.windows.get((uint64_t)pl.bwin * sizeof(Pt));
   OvfCounters* ctr = (OvfCounters*)ws.ctr.get(sizeof(OvfCounters));
   uint32_t* perm = (uint32_t*)ws.perm.get(total_b * 4);
@@ -433,7 +460,20 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   prof_end(tok_ovf, t);
   size_t red_smem = kReduceThreads * sizeof(Pt);
   const int tok_br = prof_begin(PROF_MSM_BUCKET_REDUCE, t);
-  k_msm_bucket_reduce<F><<<(pl.bwin * ngroups + 63) / 64, 64, 0, t>>>(buckets, pl, groups);
+  k_msm_wsum_level<F><<<(pl.bwin * ngroups + 63) / 64, 64, 0, t>>>(buckets, pl.nb, pl.group, 1u, (uint32_t)pl.bwin, ngroups,
+                                                                  groups, runs0);
+  {
+    const Pt* in = runs0;
+    uint32_t in_cnt = ngroups;
+    for (int l = 0; l < lv.n; l++) {
+      Pt* acc_l = upper + lv.acc_off[l];
+      Pt* run_l = acc_l + (uint64_t)pl.bwin * lv.cnt[l];
+      k_msm_wsum_level<F><<<(pl.bwin * lv.cnt[l] + 63) / 64, 64, 0, t>>>(in, in_cnt, 1u << kWsumUpperLogG, 0u, (uint32_t)pl.bwin,
+                                                                        lv.cnt[l], acc_l, run_l);
+      in = run_l;
+      in_cnt = lv.cnt[l];
+    }
+  }
   prof_end(tok_br, t);
   const int tok_sums = prof_begin(PROF_MSM_SUMS, t);
   if (two_level) {
@@ -442,12 +482,15 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   } else {
     k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, t>>>(groups, ngroups, windows);
   }
+  int log_g0 = 0;
+  while ((1u << log_g0) < pl.group) log_g0++;
+  if (lv.n) k_msm_wsum_finish<F><<<pl.bwin, kReduceThreads, red_smem, t>>>(upper, lv, (uint32_t)log_g0, windows);
   k_msm_horner<F><<<1, 128, 0, t>>>(windows, pl, (Pt*)d_out);
   prof_end(tok_sums, t);
   // join: the caller's stream waits for the tail; otherwise the result is ready when ws.e_back fires
   // (ws.wait_tail(other_stream)) and the caller's stream may run ahead with independent bulk work
   ws.hop_back(s, join);
-  prof_count_launches(two_level ? 16 : 15);
+  prof_count_launches((two_level ? 16 : 15) + lv.n + (lv.n ? 1 : 0));
   B200_CUDA(cudaGetLastError());
 }
 
@@ -481,7 +524,8 @@ struct CurveImpl : CurveBackend {
            const MsmBases* bases, bool join, int pre) override {
     if (bases && bases->group != group) throw std::runtime_error("msm: base tables belong to the other group");
     if (n >= (1ull << 31)) throw std::runtime_error("msm: n must be < 2^31");
-    MsmPlan pl = bases ? make_msm_plan_table(n, Fr::BITS, bases->c, bases->npts, 1, msm_pre_levels(n, bases->c, pre))
+    MsmPlan pl = bases ? make_msm_plan_table(n, Fr::BITS, bases->c, bases->npts, 1, msm_pre_levels(n, bases->c, pre),
+                                             bases->tstride)
                        : make_msm_plan(n, Fr::BITS, c_override);
     if (stats) *stats = MsmStats{pl.c, pl.nwin, pl.nb, pl.task, pl.group};
     if (n == 0) {
@@ -549,25 +593,26 @@ struct CurveImpl : CurveBackend {
     if (n == 0 || n >= (1ull << 31)) throw std::runtime_error("msm_sort: n must be in [1, 2^31)");
     MsmSets sets{};
     for (int j = 0; j < nsets; j++) {
-      if (bases[j]->c != bases[0]->c || bases[j]->nwin != bases[0]->nwin)
-        throw std::runtime_error("msm_sort: base sets must share the window width");
+      if (bases[j]->c != bases[0]->c || bases[j]->nwin != bases[0]->nwin || bases[j]->tstride != bases[0]->tstride)
+        throw std::runtime_error("msm_sort: base sets must share the window width and table stride");
       sets.map[j] = maps[j];
       sets.npts[j] = bases[j]->npts;
     }
-    MsmPlan pl = make_msm_plan_table(n, Fr::BITS, bases[0]->c, bases[0]->npts, nsets);
+    MsmPlan pl = make_msm_plan_table(n, Fr::BITS, bases[0]->c, bases[0]->npts, nsets, 0, bases[0]->tstride);
     msm_sort_launch<Fr>(d_scalars, pl, sets, ws, s, out);
   }
 
   void msm_reduce(int group, const MsmSorted& so, int first_set, int count, const MsmBases* const* bases,
                   void* d_out, MsmWorkspace& ws, cudaStream_t s, bool join) override {
-    if (!so.pl.table || first_set < 0 || count < 1 || first_set + count > so.pl.bwin)
+    const int ts = so.pl.tstride;
+    if (!so.pl.table || first_set < 0 || count < 1 || (first_set + count) * ts > so.pl.bwin)
       throw std::runtime_error("msm_reduce: bad set range");
     MsmSorted sub = so;
-    sub.pl = make_msm_plan_table(so.pl.n, Fr::BITS, so.pl.c, so.pl.npts, count);
-    sub.off += (uint64_t)first_set * so.pl.nb;
-    sub.end += (uint64_t)first_set * so.pl.nb;
-    sub.sorted += (uint64_t)first_set * so.pl.stride;
-    sub.totals += first_set;
+    sub.pl = make_msm_plan_table(so.pl.n, Fr::BITS, so.pl.c, so.pl.npts, count, 0, ts);
+    sub.off += (uint64_t)first_set * ts * so.pl.nb;
+    sub.end += (uint64_t)first_set * ts * so.pl.nb;
+    sub.sorted += (uint64_t)first_set * ts * so.pl.stride;
+    sub.totals += first_set * ts;
     MsmPts pts{};
     for (int j = 0; j < count; j++) {
       if (bases[j]->group != group) throw std::runtime_error("msm_reduce: base tables belong to the other group");
@@ -576,27 +621,31 @@ struct CurveImpl : CurveBackend {
     reduce_dispatch(group, sub, pts, d_out, ws, s, join);
   }
 
-  int table_window(uint64_t npts) const override { return msm_table_window(npts, Fr::BITS); }
+  int table_window(uint64_t npts, int tstride) const override { return msm_table_window(npts, Fr::BITS, tstride); }
 
   void build_tables(MsmBases& b, int group, const void* d_points, uint64_t npts, int window_bits,
-                    cudaStream_t s) override {
+                    cudaStream_t s, int tstride) override {
     b.group = group;
     b.npts = npts;
-    b.c = window_bits > 0 ? window_bits : msm_table_window(npts, Fr::BITS);
+    b.c = window_bits > 0 ? window_bits : msm_table_window(npts, Fr::BITS, tstride);
     b.nwin = msm_nwin(Fr::BITS, b.c);
-    if ((uint64_t)b.nwin * npts >= (1ull << 31)) throw std::runtime_error("base set too large for table mode");
+    b.tstride = std::max(1, std::min(tstride, b.nwin));
+    b.ntab = msm_ntables(b.nwin, b.tstride);
+    if ((uint64_t)b.ntab * npts >= (1ull << 31))
+      throw std::runtime_error("base set too large for its table depth (raise the table stride)");
     const size_t pb = affine_bytes(group);
-    void* t = b.tables.get(std::max<uint64_t>(npts, 1) * b.nwin * pb);
+    void* t = b.tables.get(std::max<uint64_t>(npts, 1) * b.ntab * pb);
     if (!npts) return;
     unsigned blocks = (unsigned)((npts + 63) / 64);
-    // scratch for the shared inversion: 3 coordinates per (window, point); freed (stream-ordered) after the kernel
+    // scratch for the shared inversion: 3 coordinates per (table, point); freed (stream-ordered) after the kernel
     DevBuf scratch;
-    void* sc = scratch.get(std::max<uint64_t>(npts * (uint64_t)(b.nwin - 1), 1) * 3 * (pb / 2));
+    void* sc = scratch.get(std::max<uint64_t>(npts * (uint64_t)(b.ntab - 1), 1) * 3 * (pb / 2));
+    const int dbls = b.c * b.tstride;   // doublings between consecutive tables
     if (group == 1)
-      k_build_tables<G1F><<<blocks, 64, 0, s>>>((const Affine<G1F>*)d_points, npts, b.c, b.nwin, (Affine<G1F>*)t,
+      k_build_tables<G1F><<<blocks, 64, 0, s>>>((const Affine<G1F>*)d_points, npts, dbls, b.ntab, (Affine<G1F>*)t,
                                                 (typename G1F::El*)sc);
     else
-      k_build_tables<G2F><<<blocks, 64, 0, s>>>((const Affine<G2F>*)d_points, npts, b.c, b.nwin, (Affine<G2F>*)t,
+      k_build_tables<G2F><<<blocks, 64, 0, s>>>((const Affine<G2F>*)d_points, npts, dbls, b.ntab, (Affine<G2F>*)t,
                                                 (typename G2F::El*)sc);
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaStreamSynchronize(s));   // the scratch buffer is released on return
@@ -799,6 +848,10 @@ struct CurveImpl : CurveBackend {
     if (phases & 1) {
       prof_count_launches(1);
       k_assemble_mul<G1F, Fr><<<2, 1, 0, s>>>((const P1*)a.ar_msm, (const P1*)a.bs1_msm, (const FrEl*)a.rs, (P1*)a.tmp);
+    }
+    if (phases & 4) {
+      prof_count_launches(1);
+      k_assemble_fold<G1F><<<1, 1, 0, s>>>((P1*)a.k_msm, (const P1*)a.tmp);
     }
     if (phases & 2) {
       prof_count_launches(1);

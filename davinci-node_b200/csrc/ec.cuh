@@ -197,6 +197,42 @@ struct EC {
     r = acc;
   }
 
+  // r = [s] p, fixed 4-bit windows: a table of 1..15 multiples (14 additions), then 4 doublings and at most one
+  // addition per window - a quarter of the additions of double-and-add.  Used by the proof assembly (one thread
+  // per multiplication; the table lives in local memory).
+  template <int NS>
+  static __device__ __noinline__ void mul_scalar_w4(Pt& r, const Pt& p, const uint32_t* s) {
+    Pt tab[16];
+    set_inf(tab[0]);
+    tab[1] = p;
+    for (int k = 2; k < 16; k++) {
+      tab[k] = tab[k >> 1];
+      if (k & 1) {
+        tab[k] = tab[k - 1];
+        add(tab[k], p);
+      } else {
+        dbl(tab[k]);
+      }
+    }
+    Pt acc;
+    set_inf(acc);
+    bool started = false;
+    for (int i = NS * 8 - 1; i >= 0; i--) {
+      if (started) {
+        dbl(acc);
+        dbl(acc);
+        dbl(acc);
+        dbl(acc);
+      }
+      uint32_t d = (s[i >> 3] >> ((i & 7) * 4)) & 15u;
+      if (d) {
+        add(acc, tab[d]);
+        started = true;
+      }
+    }
+    r = acc;
+  }
+
   // affine normalisation: x = X/ZZ, y = Y/ZZZ ; infinity -> (0, 0).  Inlined (the inversion inside
   // is the only out-of-line call) and written through a local with a single exit.
   static __device__ __forceinline__ void to_affine(Aff& r, const Pt& p) {

@@ -69,7 +69,7 @@ template <class Fr>
 __device__ __forceinline__ bool msm_load_scalar(const typename Fr::El* __restrict__ scalars, const MsmPlan& pl,
                                                 const MsmSets& sets, uint64_t i, typename Fr::El& s,
                                                 uint32_t (&pidx)[kMaxSets]) {
-  const int nsets = pl.table ? pl.bwin : 1;
+  const int nsets = pl.table ? pl.bwin / pl.tstride : 1;
   bool any = false;
 #pragma unroll
   for (int j = 0; j < kMaxSets; j++) {
@@ -93,7 +93,8 @@ template <class Fr>
 __global__ void __launch_bounds__(256)
 k_msm_hist(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ hist, MsmSets sets) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nsets = pl.table ? pl.bwin : 1;
+  const int nsets = pl.table ? pl.bwin / pl.tstride : 1;
+  const int ts = pl.tstride;
   const unsigned lane = threadIdx.x & 31u;
   typename Fr::El s;
   uint32_t pidx[kMaxSets];
@@ -108,15 +109,17 @@ k_msm_hist(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __
     if (j >= nsets) break;
     const bool in = has0 && pidx[j] != kSkip;
     const unsigned grp = same & __ballot_sync(0xffffffffu, in);
-    if (in && lane == (unsigned)(__ffs(grp) - 1)) atomicAdd(&hist[(uint64_t)j * pl.nb + b], (uint32_t)__popc(grp));
+    if (in && lane == (unsigned)(__ffs(grp) - 1)) atomicAdd(&hist[(uint64_t)(j * ts) * pl.nb + b], (uint32_t)__popc(grp));
   }
   if (!live) return;
+  int wr = 0;   // w % tstride
   for (int w = 1; w < pl.nwin; w++) {
+    if (++wr == ts) wr = 0;
     if (!dw.next(s.v, w, pl.c, b, neg)) continue;
     if (pl.table) {
 #pragma unroll
       for (int j = 0; j < kMaxSets; j++)
-        if (j < nsets && pidx[j] != kSkip) atomicAdd(&hist[(uint64_t)j * pl.nb + b], 1u);
+        if (j < nsets && pidx[j] != kSkip) atomicAdd(&hist[(uint64_t)(j * ts + wr) * pl.nb + b], 1u);
     } else {
       atomicAdd(&hist[(uint64_t)w * pl.nb + b], 1u);
     }
@@ -223,7 +226,8 @@ __global__ void __launch_bounds__(256)
 k_msm_scatter(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t* __restrict__ cur,
               uint32_t* __restrict__ sorted, MsmSets sets) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int nsets = pl.table ? pl.bwin : 1;
+  const int nsets = pl.table ? pl.bwin / pl.tstride : 1;
+  const int ts = pl.tstride;
   const unsigned lane = threadIdx.x & 31u;
   typename Fr::El s;
   uint32_t pidx[kMaxSets];
@@ -241,24 +245,29 @@ k_msm_scatter(const typename Fr::El* __restrict__ scalars, MsmPlan pl, uint32_t*
     if (in) {
       const int leader = __ffs(grp) - 1;
       uint32_t base = 0;
-      if ((int)lane == leader) base = atomicAdd(&cur[(uint64_t)j * pl.nb + b], (uint32_t)__popc(grp));
+      if ((int)lane == leader) base = atomicAdd(&cur[(uint64_t)(j * ts) * pl.nb + b], (uint32_t)__popc(grp));
       base = __shfl_sync(grp, base, leader);
       const uint32_t pos = base + __popc(grp & ((1u << lane) - 1u));
       // table mode: window 0 reads table 0 (the points themselves) at index pidx
-      sorted[(uint64_t)j * pl.stride + pos] = pidx[j] | (neg ? 0x80000000u : 0u);
+      sorted[(uint64_t)(j * ts) * pl.stride + pos] = pidx[j] | (neg ? 0x80000000u : 0u);
     }
   }
   if (!live) return;
+  int wr = 0, wq = 0;   // w % tstride, w / tstride
   for (int w = 1; w < pl.nwin; w++) {
+    if (++wr == ts) {
+      wr = 0;
+      wq++;
+    }
     if (!dw.next(s.v, w, pl.c, b, neg)) continue;
     const uint32_t sign = neg ? 0x80000000u : 0u;
     if (pl.table) {
 #pragma unroll
       for (int j = 0; j < kMaxSets; j++) {
         if (j < nsets && pidx[j] != kSkip) {
-          uint32_t pos = atomicAdd(&cur[(uint64_t)j * pl.nb + b], 1u);
-          // digit window w reads the precomputed multiple 2^(c w) P, stored at w * npts + index
-          sorted[(uint64_t)j * pl.stride + pos] = (uint32_t)((uint64_t)w * sets.npts[j] + pidx[j]) | sign;
+          uint32_t pos = atomicAdd(&cur[(uint64_t)(j * ts + wr) * pl.nb + b], 1u);
+          // digit window w = wq s + wr reads the precomputed multiple 2^(c s wq) P, stored at wq * npts + index
+          sorted[(uint64_t)(j * ts + wr) * pl.stride + pos] = (uint32_t)((uint64_t)wq * sets.npts[j] + pidx[j]) | sign;
         }
       }
     } else {
@@ -535,7 +544,7 @@ k_msm_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, const uint32_t
     // else: cannot happen (capacity covers every entry); stay correct anyway by taking the whole bucket
   }
   // DIRECT: pts.p[0] is the pre-reduced affine list (single bucket array), `start` indexes it
-  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[(pl.table && !pl.batch_n) ? w : 0]) + (DIRECT ? start : 0);
+  const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[(pl.table && !pl.batch_n) ? w / pl.tstride : 0]) + (DIRECT ? start : 0);
   const uint32_t* idx = DIRECT ? nullptr : sorted + (uint64_t)w * pl.stride + start;
   XYZZ<F> acc;
 #ifdef B200_ACC_LOCKSTEP
@@ -574,7 +583,7 @@ k_msm_ovf_accumulate(MsmPts pts, const uint32_t* __restrict__ sorted, MsmPlan pl
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     OvfTask tk = tasks[t];
     uint32_t w = tk.bucket / pl.nb;
-    const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[(pl.table && !pl.batch_n) ? w : 0]) + (DIRECT ? tk.start : 0);
+    const Affine<F>* points = reinterpret_cast<const Affine<F>*>(pts.p[(pl.table && !pl.batch_n) ? w / pl.tstride : 0]) + (DIRECT ? tk.start : 0);
     XYZZ<F> acc;
     accumulate_run<F, DIRECT>(acc, points, DIRECT ? nullptr : sorted + (uint64_t)w * pl.stride + tk.start, tk.len);
     store16(partial + t, acc);
@@ -694,34 +703,49 @@ k_msm_ovf_merge_l2(const OvfBucket* __restrict__ obuckets, const OvfCounters* __
 }
 
 // ------------------------------------------------------------------------------------ bucket reduction
-// thread (w, g): sum_{k in group g} (k+1) * B[w][k]  ->  groups[w * ngroups + g]
+// sum_k (k + 1) B_k by hierarchical running sums - two full additions per bucket and nothing else.
+//
+// Level 0 cuts the nb buckets of an array into groups of G0; thread (w, g) walks its group from the top with the
+// classic running sum and emits  acc = sum_j (j + 1) B[g G0 + j]  and  run = sum_j B[g G0 + j].  Then
+//     sum_k (k + 1) B_k = S_0 + G0 * sum_g g run_g ,      S_0 = sum_g acc_g
+// and the weighted sum over the groups' `run` values is the same problem again (weights g instead of g + 1, groups
+// of G1 = 16): level l emits acc_l / run_l from run_(l-1) until one group is left.  With T_L = S_L and
+// T_l = S_l + G_l T_(l+1) the window sum is T_0.  (Round 1 multiplied every group's run by its base with a 32-step
+// double-and-add: +57% multiplier work on top of the two additions per bucket.)
+//
+// in: `narrays` arrays of `count` points, array a at in + a * count.  off = 1 at level 0, 0 above.
 template <class F>
 __global__ void __launch_bounds__(64)
-k_msm_bucket_reduce(const XYZZ<F>* __restrict__ buckets, MsmPlan pl, XYZZ<F>* __restrict__ groups) {
+k_msm_wsum_level(const XYZZ<F>* __restrict__ in, uint32_t count, uint32_t G, uint32_t off, uint32_t narrays,
+                 uint32_t ngroups, XYZZ<F>* __restrict__ acc_out, XYZZ<F>* __restrict__ run_out) {
   using E = EC<F>;
-  uint32_t ngroups = pl.nb / pl.group;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (uint32_t)pl.bwin * ngroups) return;
+  if (t >= narrays * ngroups) return;
   uint32_t w = t / ngroups, g = t % ngroups;
-  const XYZZ<F>* B = buckets + (uint64_t)w * pl.nb + (uint64_t)g * pl.group;
+  const XYZZ<F>* X = in + (uint64_t)w * count;
+  const uint32_t first = g * G;
   XYZZ<F> run, acc;
   E::set_inf(run);
   E::set_inf(acc);
-  for (int k = (int)pl.group - 1; k >= 0; k--) {
-    XYZZ<F> b;
-    load16_rw(b, B + k);
-    E::add(run, b);
-    E::add(acc, run);
+  for (int j = (int)G - 1; j >= 0; j--) {
+    if (first + (uint32_t)j < count) {
+      XYZZ<F> b;
+      load16_rw(b, X + first + j);
+      E::add(run, b);
+    }
+    if ((uint32_t)j + off) E::add(acc, run);
   }
-  // bucket k of this group has weight g*group + k + 1 ; acc holds sum (k+1) B_k, run holds sum B_k
-  uint32_t base = g * pl.group;
-  if (base) {
-    XYZZ<F> m;
-    E::mul_u32(m, run, base);
-    E::add(acc, m);
-  }
-  store16(groups + t, acc);
+  store16(acc_out + t, acc);
+  store16(run_out + t, run);
 }
+
+constexpr int kWsumMaxLevels = 8;
+constexpr uint32_t kWsumUpperLogG = 4;   // groups of 16 above level 0: short dependent chains, the data is tiny
+struct WsumLevels {
+  int n;                               // levels above level 0
+  uint32_t acc_off[kWsumMaxLevels];    // offset of level l's acc array inside `upper` (points)
+  uint32_t cnt[kWsumMaxLevels];        // groups per bucket array at level l
+};
 
 // block b: out[b] = sum of in[b * per_slice .. (b + 1) * per_slice)   (window sums, in one or two levels)
 template <class F>
@@ -742,17 +766,61 @@ k_msm_slice_sum(const XYZZ<F>* __restrict__ in, uint32_t per_slice, XYZZ<F>* __r
   if (threadIdx.x == 0) store16(out + blockIdx.x, acc);
 }
 
+// block w: windows[w] <- S_0 + G0 * (S_1 + 16 * (S_2 + 16 * ( ... S_L)))   with S_0 already in windows[w] and
+// S_l = sum of level l's acc values of array w
+template <class F>
+__global__ void __launch_bounds__(kReduceThreads)
+k_msm_wsum_finish(const XYZZ<F>* __restrict__ upper, WsumLevels lv, uint32_t logG0, XYZZ<F>* __restrict__ windows) {
+  extern __shared__ uint4 smem_raw[];
+  XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
+  using E = EC<F>;
+  const uint32_t w = blockIdx.x;
+  XYZZ<F> T;
+  E::set_inf(T);
+  for (int l = lv.n - 1; l >= 0; l--) {
+    const XYZZ<F>* A = upper + lv.acc_off[l] + (uint64_t)w * lv.cnt[l];
+    XYZZ<F> s;
+    E::set_inf(s);
+    for (uint32_t g = threadIdx.x; g < lv.cnt[l]; g += kReduceThreads) {
+      XYZZ<F> p;
+      load16_rw(p, A + g);
+      E::add(s, p);
+    }
+    block_sum<F, kReduceThreads>(s, sm);
+    if (threadIdx.x == 0) {
+      for (uint32_t k = 0; k < kWsumUpperLogG; k++) E::dbl(T);
+      E::add(T, s);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    for (uint32_t k = 0; k < logG0; k++) E::dbl(T);
+    XYZZ<F> s0;
+    load16_rw(s0, windows + w);
+    E::add(T, s0);
+    store16(windows + w, T);
+  }
+}
+
 // windowed mode: out[0] = sum_w 2^(c w) windows[w]  (single thread; latency hidden by the other MSM streams)
-// table mode: out[j] = windows[j], one result per base set (the tables already carry the 2^(c w) factors)
+// table mode: one result per base set; with table stride 1 it is windows[j] (the tables carry the 2^(c w) factors)
 template <class F>
 __global__ void k_msm_horner(const XYZZ<F>* __restrict__ windows, MsmPlan pl, XYZZ<F>* __restrict__ out) {
   using E = EC<F>;
   if (blockIdx.x) return;
   if (pl.table) {
-    for (int j = threadIdx.x; j < pl.bwin; j += blockDim.x) {
-      XYZZ<F> ws;
-      load16_rw(ws, windows + j);
-      store16(out + j, ws);
+    // one result per base set (or per scalar vector in batched mode): sum_r 2^(c r) S_r over its tstride bucket sets
+    const int ts = pl.tstride;
+    for (int j = threadIdx.x; j < pl.bwin / ts; j += blockDim.x) {
+      XYZZ<F> acc;
+      load16_rw(acc, windows + j * ts + ts - 1);
+      for (int r = ts - 2; r >= 0; r--) {
+        for (int i = 0; i < pl.c; i++) E::dbl(acc);
+        XYZZ<F> ws;
+        load16_rw(ws, windows + j * ts + r);
+        E::add(acc, ws);
+      }
+      store16(out + j, acc);
     }
     return;
   }

@@ -18,6 +18,10 @@ constexpr int kMaxSets = 4;                // bucket sets one sorting pass can f
 //    buckets to reduce, which lets c grow (fewer point additions).  Several base sets that are multiplied
 //    by the SAME scalar vector (the A / B / K keys of a Groth16 proof all take the wire vector) share one
 //    digit/sort pass: bwin == nsets bucket sets, one per base set, each with its own index map.
+//    HBM budget knob: with table stride s only every s-th table is kept (T_q = 2^(c s q) P, ceil(nwin / s)
+//    tables); digit window w = q s + r reads table q and adds into bucket set r of its base set (s bucket
+//    sets per base set, bwin == nsets * s), and the set's result is sum_r 2^(c r) S_r - a Horner of (s - 1) c
+//    doublings of ONE point.  s = 1 is the full table mode, s = nwin degenerates to windowed Pippenger.
 struct MsmPlan {
   uint64_t n;          // number of scalars
   int c;               // window width in bits
@@ -33,14 +37,17 @@ struct MsmPlan {
   uint32_t ovf_task;   // points per overflow task (the remainder of an oversized bucket)
   uint32_t group;      // buckets per running-sum group
   uint32_t max_ovf;    // capacity of the overflow task list
-  uint64_t npts;       // table mode: points per table (index of digit window w is w*npts + i)
+  uint64_t npts;       // table mode: points per table (index of digit window w is (w / tstride)*npts + i)
   uint64_t stride;     // sorted-index entries reserved per bucket window
+  int tstride;         // table mode: table stride s (>= 1); bucket set of (base set j, window w) is j*s + w % s
 };
 
 inline int msm_nwin(int scalar_bits, int c) { return (scalar_bits + 1 + c - 1) / c; }
+inline int msm_ntables(int nwin, int tstride) { return (nwin + tstride - 1) / tstride; }
 
-// window width for a table-mode base set of npts points (fixed when the tables are built)
-inline int msm_table_window(uint64_t npts, int scalar_bits) {
+// window width for a table-mode base set of npts points (fixed when the tables are built); with table stride s the
+// bucket reduction is s times as large
+inline int msm_table_window(uint64_t npts, int scalar_bits, int tstride = 1) {
   // small base sets (e.g. the 4096-point KZG SRS) are latency-bound: every sequential point addition
   // costs ~8 us on an almost empty GPU, so take the smallest window that leaves <= ~4 points per bucket
   if (npts <= (1u << 16)) {
@@ -55,8 +62,9 @@ inline int msm_table_window(uint64_t npts, int scalar_bits) {
   for (int c = 4; c <= 22; c++) {
     int nwin = msm_nwin(scalar_bits, c);
     double nb = std::ldexp(1.0, c - 1);
-    double cost = (double)npts * nwin + nb * 2.0 * 4.0 + 3000.0 * nwin;   // adds + bucket reduction + fixed
-    if ((double)nwin * (double)npts >= 2147483648.0) continue;           // index must fit 31 bits
+    const int s = tstride < nwin ? tstride : nwin;
+    double cost = (double)npts * nwin + nb * 2.0 * 4.0 * s + 3000.0 * nwin;   // adds + bucket reduction + fixed
+    if ((double)msm_ntables(nwin, s) * (double)npts >= 2147483648.0) continue;   // index must fit 31 bits
     if (cost < best) {
       best = cost;
       best_c = c;
@@ -69,7 +77,7 @@ inline void msm_plan_finish(MsmPlan& pl) {
   pl.nb = 1u << (pl.c - 1);
   const uint64_t adds = pl.n * (uint64_t)pl.nwin;
   const uint64_t total_b = (uint64_t)pl.bwin * pl.nb;
-  uint64_t avg = adds / (pl.table ? pl.nb : total_b) + 1;
+  uint64_t avg = adds / (pl.table ? (uint64_t)pl.nb * pl.tstride : total_b) + 1;
   // large MSMs: size-sorted scheduling hides long buckets, keep overflow rare.  small MSMs: the longest
   // per-thread chain IS the latency, so cap it hard and split the rest into short parallel tasks.
   const bool small = adds < (1u << 21);
@@ -87,8 +95,9 @@ inline void msm_plan_finish(MsmPlan& pl) {
   if (g < 4) g = std::min<uint32_t>(4, pl.nb);
   pl.group = std::min<uint32_t>(g, pl.nb);
   // every overflowing bucket holds > task_min points and every overflow task but the last is full
-  pl.max_ovf = (uint32_t)((adds / pl.ovf_task + adds / pl.task_min + 2) * (pl.table ? pl.bwin : 1));
-  pl.stride = pl.table ? adds + ((uint64_t)pl.nb << pl.pre) : pl.n;
+  pl.max_ovf = (uint32_t)((adds / pl.ovf_task + adds / pl.task_min + 2) * (pl.table ? pl.bwin / pl.tstride : 1));
+  // table mode: a bucket set receives at most ceil(nwin / s) digits per scalar
+  pl.stride = pl.table ? pl.n * (uint64_t)msm_ntables(pl.nwin, pl.tstride) + ((uint64_t)pl.nb << pl.pre) : pl.n;
 }
 
 inline MsmPlan make_msm_plan(uint64_t n, int scalar_bits, int c_override) {
@@ -111,17 +120,20 @@ inline MsmPlan make_msm_plan(uint64_t n, int scalar_bits, int c_override) {
   pl.bwin = pl.nwin;
   pl.table = 0;
   pl.npts = 0;
+  pl.tstride = 1;
   msm_plan_finish(pl);
   return pl;
 }
 
-inline MsmPlan make_msm_plan_table(uint64_t n, int scalar_bits, int c, uint64_t npts, int nsets = 1, int pre = 0) {
+inline MsmPlan make_msm_plan_table(uint64_t n, int scalar_bits, int c, uint64_t npts, int nsets = 1, int pre = 0,
+                                   int tstride = 1) {
   MsmPlan pl{};
   pl.n = n;
-  pl.pre = nsets == 1 ? pre : 0;
+  pl.pre = (nsets == 1 && tstride == 1) ? pre : 0;
   pl.c = c;
   pl.nwin = msm_nwin(scalar_bits, c);
-  pl.bwin = nsets;
+  pl.tstride = tstride < 1 ? 1 : (tstride > pl.nwin ? pl.nwin : tstride);
+  pl.bwin = nsets * pl.tstride;
   pl.table = 1;
   pl.npts = npts;
   msm_plan_finish(pl);

@@ -66,9 +66,15 @@ PkSlot::~PkSlot() {
     if (e) cudaEventDestroy(e);
 }
 
-PkInstance::PkInstance(int dev) : device(dev) {
-  for (int i = 0; i < kSlotsPerDevice; i++) slots.emplace_back(new PkSlot(dev));
+PkInstance::PkInstance(int dev, int nslots) : device(dev) {
+  for (int i = 0; i < nslots; i++) slots.emplace_back(new PkSlot(dev));
 }
+
+namespace {
+std::atomic<uint64_t> g_pk_budget{0};
+}
+void set_pk_table_budget(uint64_t bytes) { g_pk_budget.store(bytes); }
+uint64_t pk_table_budget() { return g_pk_budget.load(); }
 
 PkSlot& PkInstance::acquire() {
   for (auto& s : slots)
@@ -147,10 +153,53 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
   }
   pk->total_commit = total_sigma;
 
+  int nslots = pk->n >= (1ull << 23) ? 2 : kSlotsPerDevice;
+  if (const char* e = std::getenv("B200_SLOTS")) nslots = std::max(1, std::min(8, std::atoi(e)));
   for (int dev : devices) {
     DeviceScope ds(dev);
-    std::unique_ptr<PkInstance> in(new PkInstance(dev));
+    std::unique_ptr<PkInstance> in(new PkInstance(dev, nslots));
     cudaStream_t s = in->slots[0]->st[0];
+    // ---- HBM budget policy: the smallest table stride whose window tables (plus the transient scratch of the
+    //      largest table build) fit the key's budget.  Budget: b200_set_pk_table_budget / B200_PK_BUDGET_GB, else
+    //      55% of the memory free right now minus this key's proof workspaces.
+    const uint64_t wire_pts = std::max({d.g1_A.len + 2, d.g1_B.len + 2, d.g1_K.len + 1});
+    auto tables_bytes = [&](int ts, uint64_t* peak) {
+      const int bits = cb->fr_bits();
+      auto set_bytes = [&](uint64_t npts, size_t pb, int c) {
+        return (uint64_t)msm_ntables(msm_nwin(bits, c), ts) * std::max<uint64_t>(npts, 1) * pb;
+      };
+      const int cw = cb->table_window(wire_pts, ts), cz = cb->table_window(std::max<uint64_t>(d.g1_Z.len, 1), ts);
+      uint64_t parts[6] = {set_bytes(d.g1_A.len + 2, g1b, cw), set_bytes(d.g1_B.len + 2, g1b, cw),
+                           set_bytes(d.g2_B.len + 2, g2b, cw), set_bytes(d.g1_K.len + 1, g1b, cw),
+                           set_bytes(d.g1_Z.len, g1b, cz),
+                           2 * set_bytes(total_sigma, g1b, cb->table_window(std::max<uint64_t>(total_sigma, 1), ts))};
+      uint64_t sum = 0, big = 0;
+      for (uint64_t v : parts) {
+        sum += v;
+        big = std::max(big, v);
+      }
+      *peak = sum + big + big / 2;   // staging copy + 1.5x scratch of the set being built
+      return sum;
+    };
+    {
+      uint64_t budget = pk_table_budget();
+      if (const char* e = std::getenv("B200_PK_BUDGET_GB")) budget = (uint64_t)(std::atof(e) * 1e9);
+      if (!budget) {
+        size_t free_b = 0, total_b = 0;
+        B200_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t slot_est = (uint64_t)nslots * (pk->m + 3 * pk->n) * frb * 3;   // inputs + sort / bucket workspaces
+        budget = free_b > slot_est ? (uint64_t)((free_b - slot_est) * 0.55) : 0;
+      }
+      int ts = 1;
+      if (const char* e = std::getenv("B200_TABLE_STRIDE")) {
+        ts = std::max(1, std::atoi(e));
+      } else {
+        uint64_t peak = 0;
+        while (ts < 32 && (tables_bytes(ts, &peak), peak) > budget) ts++;
+      }
+      in->tstride = ts;
+    }
+    const int ts = in->tstride;
     // upload (points || extra0 || extra1) to a staging buffer, build its window tables, drop the staging copy
     DevBuf stage;
     auto put_tables = [&](MsmBases& t, int group, const b200_slice& sl, size_t pb, const void* e0, const void* e1,
@@ -160,11 +209,12 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
       if (sl.len) B200_CUDA(cudaMemcpyAsync(p, sl.ptr, sl.len * pb, cudaMemcpyHostToDevice, s));
       if (e0) B200_CUDA(cudaMemcpyAsync(p + sl.len * pb, e0, pb, cudaMemcpyHostToDevice, s));
       if (e1) B200_CUDA(cudaMemcpyAsync(p + (sl.len + 1) * pb, e1, pb, cudaMemcpyHostToDevice, s));
-      cb->build_tables(t, group, p, cnt, window_bits, s);
+      cb->build_tables(t, group, p, cnt, window_bits, s, ts);
+      in->table_bytes += (uint64_t)t.ntab * std::max<uint64_t>(cnt, 1) * pb;
       B200_CUDA(cudaStreamSynchronize(s));   // staging buffer is reused by the next base set
     };
     // the wire-indexed keys share one digit/sort pass per proof, hence one window width
-    int cw = cb->table_window(std::max({d.g1_A.len + 2, d.g1_B.len + 2, d.g1_K.len + 1}));
+    int cw = cb->table_window(wire_pts, ts);
     if (const char* e = std::getenv("B200_WIRE_WINDOW")) {   // tuning knob: window width of the wire-indexed keys
       if (std::atoi(e) >= 4 && std::atoi(e) <= 22) cw = std::atoi(e);
     }
@@ -187,7 +237,8 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
                                     cudaMemcpyHostToDevice, s));
         off += pk->commit_n[i];
       }
-      cb->build_tables(in->tSigma, 1, sg, total_sigma, 0, s);
+      cb->build_tables(in->tSigma, 1, sg, total_sigma, 0, s, ts);
+      in->table_bytes += (uint64_t)in->tSigma.ntab * std::max<uint64_t>(total_sigma, 1) * g1b;
       B200_CUDA(cudaStreamSynchronize(s));
     }
     for (uint32_t i = 0; i < d.nb_commitments; i++) {
@@ -242,6 +293,19 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
     throw std::runtime_error("a/b/c: need equal lengths <= domain size");
   if (in.nb_commitments != commit_n.size()) throw std::runtime_error("nb_commitments mismatch with proving key");
   if (!in.r || !in.s) throw std::runtime_error("r / s missing");
+  if ((m && !in.wires.ptr) || (in.a.len && (!in.a.ptr || !in.b.ptr || !in.c.ptr)))
+    throw std::runtime_error("wires / a / b / c: null pointer");
+  // every argument is validated before the first copy is enqueued
+  if (!commit_n.empty()) {
+    if (!in.priv_committed) throw std::runtime_error("priv_committed is null but the key has commitments");
+    for (size_t i = 0; i < commit_n.size(); i++) {
+      if (in.priv_committed[i].len != commit_n[i])
+        throw std::runtime_error("private committed values: length mismatch with commitment key");
+      if (commit_n[i] && !in.priv_committed[i].ptr) throw std::runtime_error("private committed values: null pointer");
+    }
+    if (commit_n.size() > 1 && !in.fold_challenge)
+      throw std::runtime_error("fold_challenge required with more than one commitment");
+  }
   const cudaMemcpyKind kind = inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   // Streams.  sc: input copies.  Bulk (throughput-bound) kernels - sorts, bucket accumulation, NTT passes - go to
   // ONE stream per proof by default (sb == sw == sg): two different accumulation kernels sharing an SM evict each
@@ -286,13 +350,8 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   if (have_pok) {
     uint64_t off = 0;
     for (size_t i = 0; i < commit_n.size(); i++) {
-      if (in.priv_committed[i].len != commit_n[i])
-        throw std::runtime_error("private committed values: length mismatch with commitment key");
       if (commit_n[i]) B200_CUDA(cudaMemcpyAsync(cv + off * frb, in.priv_committed[i].ptr, commit_n[i] * frb, kind, sc));
-      if (i >= 1) {
-        if (!in.fold_challenge) throw std::runtime_error("fold_challenge required with more than one commitment");
-        if (i == 1) B200_CUDA(cudaMemcpyAsync(S.chal.p, in.fold_challenge, frb, kind, sc));
-      }
+      if (i == 1) B200_CUDA(cudaMemcpyAsync(S.chal.p, in.fold_challenge, frb, kind, sc));
       off += commit_n[i];
     }
   }
@@ -326,10 +385,13 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   aa.bs1_msm = mo + x1;
   aa.rs = W + m * frb;
   aa.tmp = S.tmp.p;
-  if (!d_partials) {
+  // (range-split slices do the same with their partial sums: sum_g s*Ar_g = s*Ar, so the multiplications never sit
+  // on the critical path after the gather)
+  aa.k_msm = mo + 2 * x1;
+  {
     S.ws[1].wait_tail(sh);
     const int tok_mul = prof_begin(PROF_ASSEMBLE, sh);
-    cb->assemble(aa, sh, 1);
+    cb->assemble(aa, sh, d_partials ? (1 | 4) : 1);
     prof_end(tok_mul, sh);
   }
 
@@ -352,7 +414,8 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   S.ws[2].wait_tail(sh);
   if (have_pok) S.ws[3].wait_tail(sh);
   if (d_partials) {
-    // range-split mode: hand the raw partial sums back (layout of msm_out: 5 G1 XYZZ then 1 G2 XYZZ)
+    // range-split mode: hand the partial sums back (layout of msm_out: 5 G1 XYZZ then 1 G2 XYZZ); the K slot
+    // already holds K_g + s*Ar_g + r*Bs1_g
     if (!have_pok) B200_CUDA(cudaMemsetAsync(o_pok, 0, x1, sh));
     B200_CUDA(cudaMemcpyAsync(d_partials, mo, 5 * x1 + x2, cudaMemcpyDeviceToDevice, sh));
     B200_CUDA(cudaStreamSynchronize(sh));

@@ -24,7 +24,12 @@ struct PkSlot {
   ~PkSlot();
 };
 
-constexpr int kSlotsPerDevice = 4;
+constexpr int kSlotsPerDevice = 4;        // proofs in flight per key and GPU (2 for domains >= 2^23, B200_SLOTS overrides)
+
+// HBM budget of ONE key's window tables in bytes (0 = automatic: a share of the device memory free at
+// registration).  The registration picks the smallest table stride whose tables fit (msm_plan.h).
+void set_pk_table_budget(uint64_t bytes);
+uint64_t pk_table_budget();
 
 // One copy of a proving key on one GPU.
 struct PkInstance {
@@ -37,7 +42,9 @@ struct PkInstance {
   NttDomain dom;
   std::vector<std::unique_ptr<PkSlot>> slots;
   std::atomic<uint32_t> next_slot{0};
-  explicit PkInstance(int dev);
+  int tstride = 1;           // table stride chosen for this key (HBM budget policy)
+  uint64_t table_bytes = 0;  // resident window-table bytes of this key on this GPU
+  explicit PkInstance(int dev, int nslots);
   // returns a slot with its mutex HELD (first free one, else waits on the next in round-robin order)
   PkSlot& acquire();
 };

@@ -102,3 +102,12 @@ class Blob:
         except capi.B200Error as e:
             raise BlobError(str(e)) from e
         return [bytes(out[48 * k:48 * (k + 1)]) for k in range(128)]
+
+    def ComputeCommitmentAndProof(self, device=-1):
+        """types/blobs.go:138-149: (commitment, blob proof) of a Version 0 BlobTxSidecar."""
+        commitment = self.ComputeCommitment(device)
+        return commitment, self.ComputeBlobProof(commitment, device)
+
+    def ComputeCommitmentAndCellProofs(self, device=-1):
+        """types/blobs.go:152-162: (commitment, 128 cell proofs) of a Version 1 BlobTxSidecar."""
+        return self.ComputeCommitment(device), self.ComputeCellProofs(device)

@@ -114,9 +114,13 @@ def register_key_slice(sub_pk, sub_ccs, info):
     return prover.register_proving_key(sub_pk, sub_ccs, z_offset=info["z_offset"])
 
 
-def prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_committed_dev=None):
+def prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_committed_dev=None, fold_challenge=None):
     """Partial sums of one key slice: W_dev is the FULL wire vector on this device (the slice is taken
-    here), a/b/c are full.  Returns a device tensor of 5*xyzz(1)+xyzz(2) bytes."""
+    here), a/b/c are full.  Returns a device tensor of 5*xyzz(1)+xyzz(2) bytes whose K slot already holds
+    K_g + s*Ar_g + r*Bs1_g.  fold_challenge (int) is required with more than one commitment.
+
+    The C ABI reads its device inputs on internal streams, so everything the caller produced on the current
+    torch stream (W / a / b / c, the r,s upload below) is synchronised before the call."""
     import ctypes as C
     import torch
     from . import capi
@@ -135,7 +139,13 @@ def prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_co
         pcs[i] = capi.Slice(t.data_ptr(), cnt)
     pin.priv_committed = pcs
     pin.fold_challenge = None
+    if k > 1:
+        if fold_challenge is None:
+            raise ValueError("fold_challenge is required with more than one commitment")
+        fc = torch.from_numpy(L.enc_fr([fold_challenge])).cuda()
+        pin.fold_challenge = fc.data_ptr()
     out = torch.zeros(5 * L.xyzz_bytes(1) + L.xyzz_bytes(2), dtype=torch.uint8, device="cuda")
+    torch.cuda.current_stream().synchronize()
     capi.check(capi.lib.b200_prove_partial_dev(handle, C.byref(pin), out.data_ptr(), torch.cuda.current_device()))
     return out
 
@@ -155,10 +165,10 @@ def assemble(L, partials_dev, nparts, r, s, have_pok):
 
 
 def prove_range_split(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, have_pok, priv_committed_dev=None,
-                      group=None):
+                      group=None, fold_challenge=None):
     """One proof over all ranks of `group`: partial sums on every GPU, all-gather (NCCL / NVLink), local
     assembly.  Every rank returns the same proof."""
     import torch.distributed as dist
-    part = prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_committed_dev)
+    part = prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_committed_dev, fold_challenge)
     allp = gather_partials(part, group)
     return assemble(L, allp, dist.get_world_size(group), r, s, have_pok)

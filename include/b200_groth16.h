@@ -153,6 +153,14 @@ typedef struct {
 /* Upload a proving key (replaces icicle's device-side pk setup behind prover/prover_gpu.go:24-61). */
 B200_API int b200_pk_register(const b200_pk_desc* desc, uint64_t* handle_out);
 B200_API int b200_pk_release(uint64_t handle);
+/* HBM budget policy.  A key is held as window tables T_q[i] = 2^(c s q) P_i; the table stride s trades HBM for
+ * bucket-reduction work (s = 1: ~23 GB for a 2^22 BLS12-377 key, s = 2: half of that).  Registration picks the
+ * smallest s whose tables fit `bytes` (0 = automatic: 55% of the device memory free at registration, so the three
+ * production keys loaded one after the other by sequencer/circuit_artifacts.go:39-76 co-reside on one B200).
+ * b200_pk_info: out[0] = table stride, [1] = resident table bytes on the first GPU, [2] = proofs in flight per GPU,
+ * [3] = window bits of the wire-indexed sets, [4] = window bits of Z, [5] = number of GPUs holding the key. */
+B200_API int b200_set_pk_table_budget(uint64_t bytes);
+B200_API int b200_pk_info(uint64_t handle, uint64_t out[6]);
 /* Pedersen commitment i over Basis: called from the BSB22 solver hint. */
 B200_API int b200_commit(uint64_t handle, uint32_t i, b200_slice values, void* out_g1_affine, int device);
 /* The proof: replaces groth16.Prove's computeH + MultiExp section (prover/prover_cpu.go:37,57;
@@ -165,9 +173,13 @@ B200_API int b200_prove_dev(uint64_t handle, const b200_prove_in* in, const b200
  * key (b200_pk_register with a sliced descriptor) and runs b200_prove_partial_dev on its slice of the wire
  * vector and the FULL a, b, c: it writes its six un-normalised partial sums
  *   [Ar, Bs1, K, Z, Pok (G1 XYZZ each), Bs (G2 XYZZ)]  =  5 * xyzz_bytes(1) + xyzz_bytes(2) bytes.
- * The caller all-gathers them over NVLink (NCCL cannot reduce with the group law) and any GPU finishes with
- * b200_assemble_dev, which adds the `nparts` partials per element and performs the same assembly as
- * b200_prove (s*Ar + r*Bs1, affine normalisation).  d_out: Ar | Krs | Pok (G1 affine) | Bs (G2 affine). */
+ * Every slice folds s*Ar_g + r*Bs1_g into its K partial (sum_g s*Ar_g = s*Ar), so the two scalar multiplications
+ * of the assembly run on every GPU beside its MSMs instead of after the gather.
+ * The caller all-gathers the partials over NVLink (NCCL cannot reduce with the group law) and any GPU finishes
+ * with b200_assemble_dev, which adds the `nparts` partials per element and normalises to affine.  d_r / d_s are
+ * ignored (kept for ABI stability).  d_out: Ar | Krs | Pok (G1 affine) | Bs (G2 affine).
+ * Device inputs of every `_dev` prove entry point are read on the library's own streams: they must be complete
+ * (producer stream synchronised) before the call. */
 B200_API int b200_prove_partial_dev(uint64_t handle, const b200_prove_in* in, void* d_partials_out, int device);
 B200_API int b200_assemble_dev(int curve, const void* d_partials, uint32_t nparts, const void* d_r, const void* d_s,
                                int have_pok, void* d_out, void* cuda_stream);

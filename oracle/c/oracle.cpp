@@ -205,17 +205,32 @@ struct Fp2 {
     for (int i = 1; i < NRN; i++) B::add(acc, acc, a);
     r = acc;
   }
-  static void mul(El& r, const El& a, const El& b) {
-    BEl t0, t1, t2, t3;
+  static void mul(El& r, const El& a, const El& b) {   // Karatsuba, 3 base multiplications (as gnark-crypto's E2.Mul)
+    BEl t0, t1, sa, sb;
     B::mul(t0, a.c0, b.c0);
     B::mul(t1, a.c1, b.c1);
-    B::mul(t2, a.c0, b.c1);
-    B::mul(t3, a.c1, b.c0);
+    B::add(sa, a.c0, a.c1);
+    B::add(sb, b.c0, b.c1);
+    B::mul(sa, sa, sb);
+    B::sub(sa, sa, t0);
+    B::sub(sa, sa, t1);
     mul_nrn(t1, t1);
     B::sub(r.c0, t0, t1);
-    B::add(r.c1, t2, t3);
+    r.c1 = sa;
   }
-  static void sqr(El& r, const El& a) { mul(r, a, a); }
+  static void sqr(El& r, const El& a) {   // 2 base multiplications
+    BEl m, sum, d, t;
+    B::mul(m, a.c0, a.c1);
+    B::add(sum, a.c0, a.c1);
+    mul_nrn(t, a.c1);
+    B::sub(d, a.c0, t);
+    B::mul(sum, sum, d);          // a0^2 - NRN a1^2 + (1 - NRN) a0 a1
+    BEl corr = m;
+    for (int i = 2; i < NRN; i++) B::add(corr, corr, m);   // (NRN - 1) a0 a1
+    if (NRN > 1) B::add(sum, sum, corr);
+    r.c0 = sum;
+    B::dbl(r.c1, m);
+  }
   static void set_zero(El& r) { memset(&r, 0, sizeof r); }
   static void set_one(El& r) {
     B::set_one(r.c0);
@@ -340,6 +355,82 @@ struct Curve {
     F::mul(r.x, p.x, zi2);
     F::mul(r.y, p.y, zi3);
   }
+  // extended-Jacobian bucket (x = X/ZZ, y = Y/ZZZ): gnark-crypto's g1JacExtended, mixed addition 8M + 2S
+  struct Ext {
+    El x, y, zz, zzz;
+  };
+  static void ext_set_inf(Ext& p) {
+    F::set_zero(p.x);
+    F::set_zero(p.y);
+    F::set_zero(p.zz);
+    F::set_zero(p.zzz);
+  }
+  static bool ext_is_inf(const Ext& p) { return F::is_zero(p.zz); }
+  static void ext_dbl_affine(Ext& r, const El& qx, const El& qy) {   // mdbl-2008-s-1
+    El u, v, w, s2, m, t;
+    F::dbl(u, qy);
+    F::sqr(v, u);
+    F::mul(w, u, v);
+    F::mul(s2, qx, v);
+    F::sqr(m, qx);
+    F::dbl(t, m);
+    F::add(m, m, t);
+    F::sqr(r.x, m);
+    F::sub(r.x, r.x, s2);
+    F::sub(r.x, r.x, s2);
+    F::sub(t, s2, r.x);
+    F::mul(t, m, t);
+    F::mul(u, w, qy);
+    F::sub(r.y, t, u);
+    r.zz = v;
+    r.zzz = w;
+  }
+  static void ext_madd(Ext& p, const Aff& q, bool negate) {   // madd-2008-s
+    if (aff_inf(q)) return;
+    El qy = q.y;
+    if (negate) F::neg(qy, qy);
+    if (ext_is_inf(p)) {
+      p.x = q.x;
+      p.y = qy;
+      F::set_one(p.zz);
+      F::set_one(p.zzz);
+      return;
+    }
+    El u2, s2, pp, ppp, qq, t;
+    F::mul(u2, q.x, p.zz);
+    F::mul(s2, qy, p.zzz);
+    F::sub(u2, u2, p.x);
+    F::sub(s2, s2, p.y);
+    if (F::is_zero(u2)) {
+      if (F::is_zero(s2)) ext_dbl_affine(p, q.x, qy);
+      else ext_set_inf(p);
+      return;
+    }
+    F::sqr(pp, u2);
+    F::mul(ppp, u2, pp);
+    F::mul(qq, p.x, pp);
+    F::sqr(t, s2);
+    F::sub(t, t, ppp);
+    F::sub(t, t, qq);
+    F::sub(p.x, t, qq);
+    F::sub(qq, qq, p.x);
+    F::mul(qq, s2, qq);
+    F::mul(t, p.y, ppp);
+    F::sub(p.y, qq, t);
+    F::mul(p.zz, p.zz, pp);
+    F::mul(p.zzz, p.zzz, ppp);
+  }
+  // bucket -> Jacobian for the (Jacobian) running sums
+  static void ext_to_jac(Jac& r, const Ext& p) {
+    if (ext_is_inf(p)) {
+      set_inf(r);
+      return;
+    }
+    // choose Z = ZZ (then Z^2 = ZZ^2, Z^3 = ZZ^3 = ZZZ^2):  X_j = x Z^2 = X ZZ ;  Y_j = y Z^3 = Y ZZZ
+    F::mul(r.x, p.x, p.zz);
+    F::mul(r.y, p.y, p.zzz);
+    r.z = p.zz;
+  }
   static void mul_scalar(Jac& r, const Jac& p, const u64* k, int nk) {
     Jac acc;
     set_inf(acc);
@@ -355,11 +446,15 @@ struct Curve {
 // scalars: canonical (non-Montgomery) little-endian, LS limbs each.  index_map semantics as the
 // product's (scalar i multiplies points[map[i]], 0xffffffff skips) so the prove schedule can be
 // restated with the same proving-key arrays.
+// frac_k / frac_n: only digit windows [nwin k / n, nwin (k + 1) / n) are processed - a bounded SAMPLE of the MSM for
+// the CPU baseline that runs exactly the code of its share of the full MSM (Pippenger's windows are independent).
 template <class F>
 static void msm(typename Curve<F>::Jac& out, const typename Curve<F>::Aff* pts, const u64* scal, int LS, size_t n,
-                int scalar_bits, const uint32_t* map, int threads) {
+                int scalar_bits, const uint32_t* map, int threads, int frac_k = 0, int frac_n = 1) {
   typedef Curve<F> C;
   typedef typename C::Jac Jac;
+  typedef typename C::Ext Ext;
+  const size_t lo_s = 0, hi_s = n;
   int c = 4;
   {
     double best = 1e300;
@@ -374,7 +469,7 @@ static void msm(typename Curve<F>::Jac& out, const typename Curve<F>::Aff* pts, 
   // signed digits (carry across windows)
   std::vector<int32_t> dig((size_t)nwin * n);
 #pragma omp parallel for num_threads(threads) schedule(static)
-  for (long i = 0; i < (long)n; i++) {
+  for (long i = (long)lo_s; i < (long)hi_s; i++) {
     const u64* s = scal + (size_t)i * LS;
     int carry = 0;
     bool skip = map && map[i] == 0xffffffffu;
@@ -395,28 +490,33 @@ static void msm(typename Curve<F>::Jac& out, const typename Curve<F>::Aff* pts, 
     }
   }
   std::vector<Jac> wins(nwin);
+  const int w_lo = nwin * frac_k / frac_n, w_hi = nwin * (frac_k + 1) / frac_n, w_cnt = std::max(w_hi - w_lo, 1);
   // windows in parallel; within a window the point range is split so all threads stay busy
-  int split = std::max(1, threads / nwin + (threads % nwin ? 1 : 0));
+  int split = std::max(1, threads / w_cnt + (threads % w_cnt ? 1 : 0));
   std::vector<Jac> parts((size_t)nwin * split);
+  for (auto& pj : parts) C::set_inf(pj);
 #pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
-  for (int job = 0; job < nwin * split; job++) {
+  for (int job = w_lo * split; job < w_hi * split; job++) {
     int w = job / split, part = job % split;
-    size_t lo = n * part / split, hi = n * (part + 1) / split;
-    std::vector<Jac> buckets(nb);
-    for (int b = 0; b < nb; b++) C::set_inf(buckets[b]);
+    size_t lo = lo_s + (hi_s - lo_s) * part / split, hi = lo_s + (hi_s - lo_s) * (part + 1) / split;
+    std::vector<Ext> buckets(nb);
+    for (int b = 0; b < nb; b++) C::ext_set_inf(buckets[b]);
     const int32_t* dw = dig.data() + (size_t)w * n;
     for (size_t i = lo; i < hi; i++) {
       int d = dw[i];
       if (!d) continue;
       size_t pi = map ? map[i] : i;
-      if (d > 0) C::madd(buckets[d - 1], pts[pi], false);
-      else C::madd(buckets[-d - 1], pts[pi], true);
+      if (d > 0) C::ext_madd(buckets[d - 1], pts[pi], false);
+      else C::ext_madd(buckets[-d - 1], pts[pi], true);
     }
-    Jac run, acc;
+    Jac run, acc, bj;
     C::set_inf(run);
     C::set_inf(acc);
     for (int b = nb - 1; b >= 0; b--) {
-      C::add(run, buckets[b]);
+      if (!C::ext_is_inf(buckets[b])) {
+        C::ext_to_jac(bj, buckets[b]);
+        C::add(run, bj);
+      }
       C::add(acc, run);
     }
     parts[job] = acc;
@@ -477,13 +577,24 @@ struct Ntt {
       }
     }
   }
-  static std::vector<El> powers(const El& base, size_t count) {
+  static std::vector<El> powers(const El& base, size_t count, int threads = 1) {
     std::vector<El> t(count);
-    El x;
-    Fr::set_one(x);
-    for (size_t i = 0; i < count; i++) {
-      t[i] = x;
-      Fr::mul(x, x, base);
+    const size_t chunk = (count + threads - 1) / std::max(threads, 1);
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (long c = 0; c < (long)threads; c++) {
+      size_t lo = (size_t)c * chunk, hi = std::min(count, lo + chunk);
+      if (lo >= hi) continue;
+      El x;
+      Fr::set_one(x);
+      El b = base;
+      for (size_t e = lo; e; e >>= 1) {   // x = base^lo
+        if (e & 1) Fr::mul(x, x, b);
+        Fr::sqr(b, b);
+      }
+      for (size_t i = lo; i < hi; i++) {
+        t[i] = x;
+        Fr::mul(x, x, base);
+      }
     }
     return t;
   }
@@ -496,7 +607,15 @@ struct Domain {
   size_t n;
   El omega, omega_inv, g, g_inv, n_inv, den;
   std::vector<El> tw, twi, gp, gip;   // omega^k, omega^-k (k<n/2); g^k, g^-k (k<n)
-  void init(int logn_, const El& w, const El& gg) {
+  void pointwise(El* a, El* b, El* c, int threads) {
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+      Fr::mul(a[i], a[i], b[i]);
+      Fr::sub(a[i], a[i], c[i]);
+      Fr::mul(a[i], a[i], den);
+    }
+  }
+  void init(int logn_, const El& w, const El& gg, int threads = 1) {
     logn = logn_;
     n = (size_t)1 << logn;
     omega = w;
@@ -512,15 +631,17 @@ struct Domain {
     for (int i = 0; i < logn; i++) Fr::sqr(t, t);
     Fr::sub(t, t, one);
     Fr::inv(den, t);
-    tw = Ntt<Fr>::powers(omega, std::max<size_t>(n / 2, 1));
-    twi = Ntt<Fr>::powers(omega_inv, std::max<size_t>(n / 2, 1));
-    gp = Ntt<Fr>::powers(g, n);
-    gip = Ntt<Fr>::powers(g_inv, n);
+    tw = Ntt<Fr>::powers(omega, std::max<size_t>(n / 2, 1), threads);
+    twi = Ntt<Fr>::powers(omega_inv, std::max<size_t>(n / 2, 1), threads);
+    gp = Ntt<Fr>::powers(g, n, threads);
+    gip = Ntt<Fr>::powers(g_inv, n, threads);
   }
   // gnark fft.Domain semantics
   void fft(El* a, bool inverse, bool dit, bool coset, int threads) {
-    if (!inverse && coset)
-      for (size_t i = 0; i < n; i++) Fr::mul(a[i], a[i], gp[dit ? brev((uint32_t)i, logn) : i]);
+    if (!inverse && coset) {
+#pragma omp parallel for num_threads(threads) schedule(static)
+      for (long i = 0; i < (long)n; i++) Fr::mul(a[i], a[i], gp[dit ? brev((uint32_t)i, logn) : (size_t)i]);
+    }
     if (dit) Ntt<Fr>::dit(a, logn, inverse ? twi : tw, threads);
     else Ntt<Fr>::dif(a, logn, inverse ? twi : tw, threads);
     if (inverse) {
@@ -615,7 +736,7 @@ static int dispatch_fft(void* data, int logn, const void* omega, const void* g, 
   Cfg::init();
   typedef typename Cfg::FR FR;
   Domain<FR> d;
-  d.init(logn, *(const typename FR::El*)omega, *(const typename FR::El*)g);
+  d.init(logn, *(const typename FR::El*)omega, *(const typename FR::El*)g, threads);
   d.fft((typename FR::El*)data, inverse, dit, coset, threads);
   return 0;
 }
@@ -625,14 +746,19 @@ static int dispatch_h(void* a, void* b, void* c, int logn, const void* omega, co
   Cfg::init();
   typedef typename Cfg::FR FR;
   Domain<FR> d;
-  d.init(logn, *(const typename FR::El*)omega, *(const typename FR::El*)g);
+  d.init(logn, *(const typename FR::El*)omega, *(const typename FR::El*)g, threads);
   d.compute_h((typename FR::El*)a, (typename FR::El*)b, (typename FR::El*)c, threads);
   return 0;
 }
 
 // The Prove MSM schedule with the same extended-array / index-map convention as the product
 // (A_ext = A || delta || alpha with scalars W || r || s || 1 || -rs, see prover.cu), so one set of
-// proving-key buffers feeds both.  Outputs affine Ar, Bs, Krs.
+// proving-key buffers feeds both.  Outputs affine Ar, Bs, Krs (and Pok when a sigma basis is given).
+// nparts == 10 turns the call into a bounded SAMPLE of the proof for the CPU baseline: component `part` of
+//   0: quotient H (7 transforms) + PoK MSM + assembly   1: MSM A   2: MSM B1   3, 4: halves of the G2 MSM (by window
+//   range)   5: MSM K   6..9: quarters of the quotient MSM Z (by window range)
+// each running exactly the code the full proof runs for it; the outputs are then meaningless.  comp_seconds (7
+// doubles, optional) receives the wall time of H, A, B1, B2, K, Z, PoK + assembly.
 struct ProveArgs {
   int curve, logn;
   const void *omega, *g;
@@ -643,6 +769,13 @@ struct ProveArgs {
   void *a, *b, *c;            // n scalars each (overwritten)
   void *out_ar, *out_bs, *out_krs;
   int threads;
+  // --- appended in round 2 (zero = absent)
+  const void* sigma;          // BasisExpSigma points of the commitment (n_commit)
+  const void* cvals;          // committed wire values (Montgomery)
+  uint64_t n_commit;
+  void* out_pok;
+  int part, nparts;
+  double* comp_seconds;
 };
 
 template <class Cfg>
@@ -653,9 +786,26 @@ static int prove_impl(const ProveArgs& p) {
   typedef Curve<typename Cfg::G2F> C2;
   constexpr int LS = sizeof(typename FR::El) / 8;
   const int T = p.threads;
-  Domain<FR> d;
-  d.init(p.logn, *(const typename FR::El*)p.omega, *(const typename FR::El*)p.g);
-  d.compute_h((typename FR::El*)p.a, (typename FR::El*)p.b, (typename FR::El*)p.c, T);
+  const bool sample = p.nparts > 1;
+  if (sample && p.nparts != 10) return -2;
+  auto on = [&](int first, int last) { return !sample || (p.part >= first && p.part <= last); };
+  double ts[7] = {0, 0, 0, 0, 0, 0, 0};
+  typename FR::El* va = (typename FR::El*)p.a;
+  typename FR::El* vb = (typename FR::El*)p.b;
+  typename FR::El* vc = (typename FR::El*)p.c;
+  double t0 = omp_get_wtime();
+  if (on(0, 0)) {
+    // gnark keeps the domain's twiddle tables in the proving key (fft.NewDomain at setup): build them once per
+    // (curve, size) and keep them across proofs
+    static Domain<FR> d;
+    static int d_logn = -1;
+    if (d_logn != p.logn || !FR::eq(d.omega, *(const typename FR::El*)p.omega) || !FR::eq(d.g, *(const typename FR::El*)p.g)) {
+      d.init(p.logn, *(const typename FR::El*)p.omega, *(const typename FR::El*)p.g, T);
+      d_logn = p.logn;
+    }
+    d.compute_h(va, vb, vc, T);
+  }
+  ts[0] = omp_get_wtime() - t0;
   auto canon = [&](const void* mont, size_t n) {
     std::vector<u64> v(n * LS);
 #pragma omp parallel for num_threads(T) schedule(static)
@@ -666,24 +816,137 @@ static int prove_impl(const ProveArgs& p) {
     }
     return v;
   };
-  std::vector<u64> w = canon(p.W_ext, p.m + 4), h = canon(p.a, p.nZ);
-  typename C1::Jac ar, bs1, k, z;
+  typename C1::Jac ar, bs1, k, z, pok;
   typename C2::Jac bs2;
-  msm<typename Cfg::G1F>(ar, (const typename C1::Aff*)p.A_ext, w.data(), LS, p.m + 4, FR::P.bits, p.mapA, T);
-  msm<typename Cfg::G1F>(bs1, (const typename C1::Aff*)p.B1_ext, w.data(), LS, p.m + 4, FR::P.bits, p.mapB, T);
-  msm<typename Cfg::G2F>(bs2, (const typename C2::Aff*)p.B2_ext, w.data(), LS, p.m + 4, FR::P.bits, p.mapB, T);
-  msm<typename Cfg::G1F>(k, (const typename C1::Aff*)p.K_ext, w.data() + p.nb_public * LS, LS,
-                         p.m - p.nb_public + 4, FR::P.bits, p.mapK, T);
-  msm<typename Cfg::G1F>(z, (const typename C1::Aff*)p.Z, h.data(), LS, p.nZ, FR::P.bits, nullptr, T);
-  typename C1::Jac t0, t1;
-  C1::mul_scalar(t0, ar, w.data() + (p.m + 1) * LS, LS);    // s * Ar
-  C1::mul_scalar(t1, bs1, w.data() + (p.m + 0) * LS, LS);   // r * Bs1
-  C1::add(k, z);
-  C1::add(k, t0);
-  C1::add(k, t1);
-  C1::to_affine(*(typename C1::Aff*)p.out_ar, ar);
-  C2::to_affine(*(typename C2::Aff*)p.out_bs, bs2);
-  C1::to_affine(*(typename C1::Aff*)p.out_krs, k);
+  const size_t nw = p.m + 4, nk = p.m - p.nb_public + 4;
+  std::vector<u64> w;
+  if (on(0, 5)) w = canon(p.W_ext, nw);
+  t0 = omp_get_wtime();
+  if (on(1, 1)) msm<typename Cfg::G1F>(ar, (const typename C1::Aff*)p.A_ext, w.data(), LS, nw, FR::P.bits, p.mapA, T);
+  ts[1] = omp_get_wtime() - t0;
+  t0 = omp_get_wtime();
+  if (on(2, 2)) msm<typename Cfg::G1F>(bs1, (const typename C1::Aff*)p.B1_ext, w.data(), LS, nw, FR::P.bits, p.mapB, T);
+  ts[2] = omp_get_wtime() - t0;
+  t0 = omp_get_wtime();
+  if (on(3, 4))
+    msm<typename Cfg::G2F>(bs2, (const typename C2::Aff*)p.B2_ext, w.data(), LS, nw, FR::P.bits, p.mapB, T,
+                           sample ? p.part - 3 : 0, sample ? 2 : 1);
+  ts[3] = omp_get_wtime() - t0;
+  t0 = omp_get_wtime();
+  if (on(5, 5))
+    msm<typename Cfg::G1F>(k, (const typename C1::Aff*)p.K_ext, w.data() + p.nb_public * LS, LS, nk, FR::P.bits, p.mapK, T);
+  ts[4] = omp_get_wtime() - t0;
+  t0 = omp_get_wtime();
+  if (on(6, 9)) {
+    std::vector<u64> h = canon(p.a, p.nZ);
+    msm<typename Cfg::G1F>(z, (const typename C1::Aff*)p.Z, h.data(), LS, p.nZ, FR::P.bits, nullptr, T,
+                           sample ? p.part - 6 : 0, sample ? 4 : 1);
+  }
+  ts[5] = omp_get_wtime() - t0;
+  t0 = omp_get_wtime();
+  if (on(0, 0) && p.sigma && p.n_commit) {
+    std::vector<u64> cv = canon(p.cvals, p.n_commit);
+    msm<typename Cfg::G1F>(pok, (const typename C1::Aff*)p.sigma, cv.data(), LS, p.n_commit, FR::P.bits, nullptr, T);
+    if (p.out_pok) C1::to_affine(*(typename C1::Aff*)p.out_pok, pok);
+  }
+  if (!sample) {
+    typename C1::Jac t0j, t1j;
+    C1::mul_scalar(t0j, ar, w.data() + (p.m + 1) * LS, LS);    // s * Ar
+    C1::mul_scalar(t1j, bs1, w.data() + (p.m + 0) * LS, LS);   // r * Bs1
+    C1::add(k, z);
+    C1::add(k, t0j);
+    C1::add(k, t1j);
+    C1::to_affine(*(typename C1::Aff*)p.out_ar, ar);
+    C2::to_affine(*(typename C2::Aff*)p.out_bs, bs2);
+    C1::to_affine(*(typename C1::Aff*)p.out_krs, k);
+  }
+  ts[6] = omp_get_wtime() - t0;
+  if (p.comp_seconds) memcpy(p.comp_seconds, ts, sizeof ts);
+  return 0;
+}
+
+// out[i] = [k0 + i] G as affine points (Montgomery): valid, distinct subgroup points for the CPU baseline's
+// synthetic key.  Blocks of B points Q_j + T_i (Q_j = [k0 + j B] G, T_i = [i] G) share one field inversion.
+template <class Cfg, class F>
+static void gen_points_impl(const void* gen_affine, uint64_t k0, size_t n, void* out_v, int threads) {
+  typedef Curve<F> C;
+  typedef typename C::Aff Aff;
+  typedef typename C::Jac Jac;
+  typedef typename F::El El;
+  const size_t B = 256;
+  Aff* out = (Aff*)out_v;
+  const Aff g = *(const Aff*)gen_affine;
+  Jac gj;
+  gj.x = g.x;
+  gj.y = g.y;
+  F::set_one(gj.z);
+  // T_i = [i] G, i < B (T_0 = infinity)
+  std::vector<Aff> Tt(B);
+  {
+    Jac acc;
+    C::set_inf(acc);
+    for (size_t i = 0; i < B; i++) {
+      C::to_affine(Tt[i], acc);
+      C::add(acc, gj);
+    }
+  }
+  const size_t nblocks = (n + B - 1) / B;
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (long j = 0; j < (long)nblocks; j++) {
+    u64 kk[1] = {k0 + (u64)j * B};
+    Jac qj;
+    C::mul_scalar(qj, gj, kk, 1);
+    Aff q;
+    C::to_affine(q, qj);
+    const size_t cnt = std::min(B, n - (size_t)j * B);
+    // affine additions q + T_i, i = 1 .. cnt-1, with Montgomery's batch inversion of (x_T - x_q)
+    std::vector<El> dx(cnt), pre(cnt);
+    El run;
+    F::set_one(run);
+    for (size_t i = 1; i < cnt; i++) {
+      F::sub(dx[i], Tt[i].x, q.x);
+      pre[i] = run;
+      F::mul(run, run, dx[i]);
+    }
+    El inv;
+    F::inv(inv, run);
+    out[(size_t)j * B] = q;
+    for (size_t i = cnt - 1; i >= 1; i--) {
+      El dinv, lam, t, x3, y3;
+      F::mul(dinv, inv, pre[i]);
+      F::mul(inv, inv, dx[i]);
+      F::sub(t, Tt[i].y, q.y);
+      F::mul(lam, t, dinv);
+      F::sqr(x3, lam);
+      F::sub(x3, x3, q.x);
+      F::sub(x3, x3, Tt[i].x);
+      F::sub(t, q.x, x3);
+      F::mul(y3, lam, t);
+      F::sub(y3, y3, q.y);
+      out[(size_t)j * B + i].x = x3;
+      out[(size_t)j * B + i].y = y3;
+    }
+  }
+}
+
+template <class Cfg>
+static int dispatch_gen(int group, const void* gen, uint64_t k0, size_t n, void* out, int threads) {
+  Cfg::init();
+  if (group == 1) gen_points_impl<Cfg, typename Cfg::G1F>(gen, k0, n, out, threads);
+  else gen_points_impl<Cfg, typename Cfg::G2F>(gen, k0, n, out, threads);
+  return 0;
+}
+
+template <class Cfg>
+static int fr_mul_impl(const void* a, const void* b, void* out, uint64_t n, int to_mont, int threads) {
+  Cfg::init();
+  typedef typename Cfg::FR FR;
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (long i = 0; i < (long)n; i++) {
+    typename FR::El x = ((const typename FR::El*)a)[i];
+    if (to_mont) FR::to_mont(((typename FR::El*)out)[i], x);
+    else FR::mul(((typename FR::El*)out)[i], x, ((const typename FR::El*)b)[i]);
+  }
   return 0;
 }
 
@@ -731,13 +994,31 @@ int oc_prove(const ProveArgs* p) {
 #undef CALL
 }
 
-// element-wise Montgomery product (used by the oracle self-test)
+// element-wise Montgomery product (used by the oracle self-test and the CPU baseline's c = a * b)
 int oc_fr_mul(int curve, const void* a, const void* b, void* out, uint64_t n) {
-  switch (curve) {
-    case 1: Bn254::init(); for (uint64_t i = 0; i < n; i++) Bn254::FR::mul(((Bn254::FR::El*)out)[i], ((const Bn254::FR::El*)a)[i], ((const Bn254::FR::El*)b)[i]); return 0;
-    case 4: Bw6::init(); for (uint64_t i = 0; i < n; i++) Bw6::FR::mul(((Bw6::FR::El*)out)[i], ((const Bw6::FR::El*)a)[i], ((const Bw6::FR::El*)b)[i]); return 0;
-    default: return -1;
-  }
+  const int threads = omp_get_num_procs();
+#define CALL(C) fr_mul_impl<C>(a, b, out, n, 0, threads)
+  DISPATCH(curve, CALL)
+#undef CALL
 }
+
+// canonical -> Montgomery, element-wise
+int oc_fr_to_mont(int curve, const void* a, void* out, uint64_t n, int threads) {
+  if (threads <= 0) threads = omp_get_num_procs();
+#define CALL(C) fr_mul_impl<C>(a, nullptr, out, n, 1, threads)
+  DISPATCH(curve, CALL)
+#undef CALL
+}
+
+// out[i] = [k0 + i] gen  (affine, Montgomery; gen must not be a small-order point and k0 + n must stay far below r)
+int oc_gen_points(int curve, int group, const void* gen_affine, uint64_t k0, uint64_t n, void* out, int threads) {
+  if (threads <= 0) threads = omp_get_num_procs();
+  if (group != 1 && group != 2) return -1;
+#define CALL(C) dispatch_gen<C>(group, gen_affine, k0, (size_t)n, out, threads)
+  DISPATCH(curve, CALL)
+#undef CALL
+}
+
+int oc_num_procs(void) { return omp_get_num_procs(); }
 
 }  // extern "C"

@@ -70,6 +70,48 @@ def test_prove_bit_exact_and_verifies(env, cname, ncons, npub, ncommit, npc, mix
         prover.release_proving_key(pk)
 
 
+@pytest.mark.parametrize("case,stride", [(0, 2), (2, 3), (4, 2), (1, 32)])
+def test_prove_with_table_stride(env, monkeypatch, case, stride):
+    """HBM budget knob: with table stride s only every s-th window table is resident (s bucket sets per base set and a
+    final Horner); the proof bytes do not change."""
+    monkeypatch.setenv("B200_TABLE_STRIDE", str(stride))
+    test_prove_bit_exact_and_verifies(env, *CASES[case])
+
+
+def test_pk_table_budget_policy(env):
+    """b200_set_pk_table_budget: a key registered under a tiny budget gets a large table stride (few resident tables),
+    under a generous one stride 1; both prove the same bytes."""
+    from oracle_bridge import ccs_from_oracle, pk_from_oracle
+    capi, layout, prover, T = env
+    cx = OC.ctx("bn254")
+    q = cx.r
+    L = layout.Layout("bn254")
+    rnd = random.Random(77)
+    cs, W0 = OG.synthetic_circuit(40, 4, q, seed=9, n_commit=1, n_private_committed=3)
+    tox = OG.Toxic(*(rnd.randrange(1, q) for _ in range(5)), sigmas=[rnd.randrange(1, q)])
+    opk, ex = OG.setup(cs, cx, tox)
+    ccs = ccs_from_oracle(cs, L.id)
+    w = T.Witness(L.id, W0[1:cs.nb_public], W0[cs.nb_public:cs.nb_public + ccs.nb_secret])
+    r, s = rnd.randrange(q), rnd.randrange(q)
+    prover.SetRandomness(lambda cid: (r, s))
+    proofs, infos = [], []
+    try:
+        for budget in (1, 1 << 40):
+            capi.check(capi.lib.b200_set_pk_table_budget(budget))
+            pk = pk_from_oracle(opk, L.id)
+            try:
+                proofs.append(prover.ProveWithWitness(L.id, ccs, pk, w).points())
+                infos.append(capi.pk_info(prover.register_proving_key(pk, ccs)))
+            finally:
+                prover.release_proving_key(pk)
+    finally:
+        capi.check(capi.lib.b200_set_pk_table_budget(0))
+        prover.SetRandomness(None)
+    assert infos[0]["table_stride"] > 1 and infos[1]["table_stride"] == 1
+    assert infos[0]["table_bytes"] < infos[1]["table_bytes"]
+    assert proofs[0] == proofs[1]
+
+
 def test_prove_rejects_unsatisfied_witness(env):
     from oracle_bridge import ccs_from_oracle, pk_from_oracle
     capi, layout, prover, T = env

@@ -93,8 +93,9 @@ def test_bench_reference_arm_contract_and_no_cpu_fallback():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--logn", "12", "--cpu-logn", "10"], capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, OMP_NUM_THREADS="1")      # what torchrun sets: the arm must ignore it
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "10", "--warmup", "1",
+                        "--logn", "12"], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -102,8 +103,20 @@ def test_bench_reference_arm_contract_and_no_cpu_fallback():
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    cb = d["cpu_baseline"]
+    assert d["impl"] == "reference" and cb["kind"] == "port" and d["steps"] == 10 and d["warmup"] == 1
+    assert cb["cores"] == len(os.sched_getaffinity(0))
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
+    # the warm-up step proved the whole workload once; ten component samples add up to one proof
+    assert cb["full_proof_seconds"] > 0 and abs(cb["proofs_equivalent_timed"] - 1.0) < 1e-9
+    # the arm never maps the product library (the driver records the .so files each arm loads)
+    probe = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--logn', '10'];"
+             "runpy.run_path(%r, run_name='__main__');"
+             "maps = open('/proc/self/maps').read();"
+             "assert 'libb200groth16' not in maps and 'liboracle_c' in maps;"
+             "assert not any(m.startswith('davinci_node_b200') for m in sys.modules)") % os.path.join(root, "bench.py")
+    r = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
     import torch
     if not torch.cuda.is_available():
         r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1", "--logn", "10"],

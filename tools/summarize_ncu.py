@@ -3,6 +3,10 @@
 
   python tools/summarize_ncu.py launches <launches.csv> <out.md> [title]
   python tools/summarize_ncu.py full <report.ncu-rep> <out.md> [title]
+  python tools/summarize_ncu.py facts <report.ncu-rep> <out.json> <key>=<points> [...]
+      per-launch facts bench.py cites (profiles/r2_ncu_facts.json): for every <key> (e.g. k_msm_accumulate_g1) the
+      first kernel whose name matches the key's pattern gives dram bytes, fmaheavy %, duration; <points> = the
+      number of base points that launch processed
 """
 import collections
 import csv
@@ -71,7 +75,52 @@ def full(path, out, title):
             fh.write("\n")
 
 
+FACT_PATTERNS = {"k_msm_accumulate_g1": ("k_msm_accumulate<", "FpT<"), "k_msm_accumulate_g2": ("k_msm_accumulate<", "Fp2T<"),
+                 "k_ntt_pass": ("k_ntt_pass<", ""), "k_ntt_fused": ("k_ntt_fused", "")}
+
+
+def facts(path, out, specs):
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]
+    idx = {h: i for i, h in enumerate(hdr)}
+    res = json.load(open(out)) if os.path.exists(out) else {}
+
+    def num(r, k):
+        try:
+            return float(r[idx[k]].replace(",", ""))
+        except (KeyError, ValueError):
+            return None
+
+    units = rows[1]
+
+    def to_bytes(r, k):
+        v = num(r, k)
+        if v is None:
+            return None
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(units[idx[k]], 1)
+
+    for spec in specs:
+        key, pts = spec.split("=")
+        a, b = FACT_PATTERNS[key]
+        for r in rows[2:]:
+            name = r[idx["Kernel Name"]]
+            if a in name and b in name.split("(")[0]:
+                rd, wr = to_bytes(r, "dram__bytes_read.sum"), to_bytes(r, "dram__bytes_write.sum")
+                res[key] = {"points": int(pts), "dram_bytes": (rd or 0) + (wr or 0), "dram_read": rd, "dram_write": wr,
+                            "fmaheavy_pct": num(r, "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                            "registers": num(r, "launch__registers_per_thread"), "source": os.path.basename(path),
+                            "kernel": name.split("(")[0][:100]}
+                break
+    json.dump(res, open(out, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "facts":
+        facts(sys.argv[2], sys.argv[3], sys.argv[4:])
+        sys.exit(0)
     mode, path, out = sys.argv[1:4]
     title = sys.argv[4] if len(sys.argv) > 4 else path
     (launches if mode == "launches" else full)(path, out, title)
