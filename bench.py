@@ -274,6 +274,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-uniform", action="store_true", help="skip the uniform-random variant of the headline line")
+    ap.add_argument("--no-shard-quotient", action="store_true", help="range-split: every GPU computes the whole quotient")
+    ap.add_argument("--dump-timeline", default=None, help="range-split: write rank 0's phase timeline of one proof (JSON)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -678,7 +680,8 @@ def range_split_arm(args, cfg_name, logn, rank, local_rank, world):
             capi.check(lib.b200_prove_dev(h, C.byref(pin), C.byref(pout), local_rank))
             return out
         pc = [(Wd[c0 * frb:(c0 + wl.n_c) * frb], wl.n_c)]
-        return multi.prove_range_split(h, L, info, Wd, ad, bd, cd, wl.nc, r, s, True, pc)
+        return multi.prove_range_split(h, L, info, Wd, ad, bd, cd, wl.nc, r, s, True, pc,
+                                       shard_quotient=not args.no_shard_quotient)
 
     if world == 1:
         prove.single = wl.prove_args(sol, r, s, on_device=True)
@@ -716,6 +719,27 @@ def range_split_arm(args, cfg_name, logn, rank, local_rank, world):
     step_host(0)
     ms_e2e = timed(step_host, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    timeline = None
+    if args.dump_timeline:
+        TAGS = {0: "acc_g1", 1: "acc_g2", 2: "ntt_pass", 3: "msm_total_g1", 4: "msm_total_g2", 5: "sort", 6: "sched",
+                7: "ovf", 8: "bucket_reduce", 9: "sums", 10: "inputs", 11: "assemble", 12: "pre_reduce"}
+        barrier()
+        capi.check(lib.b200_profile_enable(1))
+        t0 = time.perf_counter()
+        step_dev(0)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        cap = 4096
+        buf = (C.c_double * (4 * cap))()
+        nrec = C.c_uint64(0)
+        capi.check(lib.b200_profile_timeline(buf, cap, C.byref(nrec)))
+        capi.check(lib.b200_profile_enable(0))
+        recs = [{"phase": TAGS.get(int(buf[4 * i]), str(int(buf[4 * i]))), "stream": int(buf[4 * i + 1]),
+                 "start_ms": buf[4 * i + 2], "end_ms": buf[4 * i + 3]} for i in range(nrec.value)]
+        timeline = {"rank": rank, "wall_ms": wall_ms, "records": recs}
+        if rank == 0:
+            json.dump(timeline, open(args.dump_timeline, "w"))
+        barrier()
     if rank == 0:
         part_bytes = 5 * L.xyzz_bytes(1) + L.xyzz_bytes(2)
         config = {"workload": workload_text(cfg_name, wl, args.mix),
@@ -732,7 +756,9 @@ def range_split_arm(args, cfg_name, logn, rank, local_rank, world):
                         "h2d_bytes_per_step": wl.h2d_bytes() * world + (131072 * 3 if with_blob else 0),
                         "d2h_bytes_per_step": wl.d2h_bytes() + (48 * 131 + 32 if with_blob else 0), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks,
-                "collective": {"op": "all_gather", "bytes_per_rank": part_bytes, "per_step": 1} if world > 1 else None}
+                "collective": ({"op": "all_gather", "bytes_per_rank": part_bytes, "per_step": 1,
+                                "quotient": ("sharded: 3 NCCL broadcasts of %d MB (coset evaluations of a, b, c) per proof" % (wl.n * frb // 1000000))
+                                if not args.no_shard_quotient else "every GPU computes the whole quotient"} if world > 1 else None)}
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_reference_run(cfg_name, logn, args.mix, 0, 1, args.cpu_parts)
             line["cpu_baseline"] = cb

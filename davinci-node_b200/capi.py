@@ -46,7 +46,7 @@ class PkDesc(C.Structure):
 class ProveIn(C.Structure):
     _fields_ = [
         ("wires", Slice), ("a", Slice), ("b", Slice), ("c", Slice), ("r", _vp), ("s", _vp),
-        ("nb_commitments", _u32), ("priv_committed", C.POINTER(Slice)), ("fold_challenge", _vp),
+        ("nb_commitments", _u32), ("priv_committed", C.POINTER(Slice)), ("fold_challenge", _vp), ("abc_form", _u32),
     ]
 
 
@@ -76,6 +76,7 @@ _PROTOS = {
     "b200_profile_collect": (_i, [C.POINTER(C.c_double), C.POINTER(_u64)]),
     "b200_profile_timeline": (_i, [C.POINTER(C.c_double), _u64, C.POINTER(_u64)]),
     "b200_prove_partial_dev": (_i, [_u64, C.POINTER(ProveIn), _vp, _i]),
+    "b200_pk_coset_evals_dev": (_i, [_u64, _vp, _i, _vp]),
     "b200_assemble_dev": (_i, [_i, _vp, _u32, _vp, _vp, _i, _vp, _vp]),
     "b200_kzg_srs_register": (_i, [_vp, _u32, C.POINTER(_u64)]),
     "b200_kzg_srs_release": (_i, [_u64]),

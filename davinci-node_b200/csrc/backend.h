@@ -198,6 +198,11 @@ struct CurveBackend {
   virtual void ntt(NttDomain& d, void* d_data, bool inverse, bool dit, bool coset, cudaStream_t s) = 0;
   // a <- h = ((a*b - c) / Z) coefficients in bit-reversed order (gnark computeH); a, b, c natural order, length n
   virtual void compute_h(NttDomain& d, void* d_a, void* d_b, void* d_c, cudaStream_t s) = 0;
+  // the two halves of compute_h, for a quotient sharded over GPUs (range-split proving): coset_evals turns ONE of
+  // a / b / c (natural order, zero padded) into its evaluations on the coset g<omega> (inverse DIF, coset DIT);
+  // compute_h_tail takes the three evaluation vectors to h (pointwise (a*b - c)/(g^n - 1), inverse coset DIF)
+  virtual void coset_evals(NttDomain& d, void* d_v, cudaStream_t s) = 0;
+  virtual void compute_h_tail(NttDomain& d, void* d_a, void* d_b, void* d_c, cudaStream_t s) = 0;
   virtual void scale_vec(void* d_x, const void* d_c, uint64_t n, cudaStream_t s) = 0;
   // writes r, s, 1, -r*s (Montgomery) to d_out[0..4) from canonical-or-Montgomery inputs already on device
   virtual void prep_rs(const void* d_r, const void* d_s, void* d_out4, cudaStream_t s) = 0;

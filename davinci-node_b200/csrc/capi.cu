@@ -402,6 +402,16 @@ int b200_prove_partial_dev(uint64_t h, const b200_prove_in* in, void* d_partials
   });
 }
 
+int b200_pk_coset_evals_dev(uint64_t h, void* d_vec, int device, void* stream) {
+  return guarded([&] {
+    if (!d_vec) throw std::runtime_error("null argument");
+    auto pk = find_pk(h);
+    PkInstance& I = pk->pick(device);
+    DeviceGuard dg(I.device);
+    pk->cb->coset_evals(I.dom, d_vec, (cudaStream_t)stream);
+  });
+}
+
 int b200_assemble_dev(int curve_id, const void* d_partials, uint32_t nparts, const void* d_r, const void* d_s,
                       int have_pok, void* d_out, void* stream) {
   return guarded([&] {

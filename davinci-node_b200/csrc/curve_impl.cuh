@@ -348,25 +348,13 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   // window sums run in one or two slice-sum levels
   const uint32_t kSlices = 64;
   const bool two_level = ngroups >= 4 * kSlices;
-  // hierarchical running sums (msm.cuh): level 0 emits acc / run per group of pl.group buckets, the levels above
-  // reduce the run values in groups of 16 until one group is left
-  WsumLevels lv{};
-  uint64_t upper_pts = 0;
-  {
-    uint32_t cnt = ngroups;
-    while (cnt > 1) {
-      if (lv.n >= kWsumMaxLevels) throw std::runtime_error("msm: bucket reduction depth");
-      cnt = (cnt + (1u << kWsumUpperLogG) - 1) >> kWsumUpperLogG;
-      lv.acc_off[lv.n] = (uint32_t)upper_pts;
-      lv.cnt[lv.n] = cnt;
-      upper_pts += 2ull * pl.bwin * cnt;   // acc | run of the level
-      lv.n++;
-    }
-  }
-  Pt* groups = (Pt*)ws.groups.get(((uint64_t)2 * pl.bwin * ngroups + (uint64_t)pl.bwin * kSlices + upper_pts) * sizeof(Pt));
-  Pt* runs0 = groups + (uint64_t)pl.bwin * ngroups;
-  Pt* mids = runs0 + (uint64_t)pl.bwin * ngroups;
-  Pt* upper = mids + (uint64_t)pl.bwin * kSlices;
+  // bucket reduction workspace (msm.cuh): [acc | ping | pong] of bwin * ngroups points each, then the block sums
+  const uint64_t arr_pts = (uint64_t)pl.bwin * ngroups;
+  Pt* groups = (Pt*)ws.groups.get((3 * arr_pts + (uint64_t)2 * pl.bwin * (kSlices + 1)) * sizeof(Pt));
+  Pt* ping = groups + arr_pts;
+  Pt* pong = ping + arr_pts;
+  Pt* mids = pong + arr_pts;                                  // 2 bwin arrays x kSlices slice sums
+  Pt* sums = mids + (uint64_t)2 * pl.bwin * kSlices;          // 2 bwin totals: [sum acc | sum g run]
   Pt* windows = (Pt*)ws.windows.get((uint64_t)pl.bwin * sizeof(Pt));
   OvfCounters* ctr = (OvfCounters*)ws.ctr.get(sizeof(OvfCounters));
   uint32_t* perm = (uint32_t*)ws.perm.get(total_b * 4);
@@ -460,37 +448,33 @@ void msm_reduce_launch(const MsmSorted& so, const MsmPts& pts, void* d_out, MsmW
   prof_end(tok_ovf, t);
   size_t red_smem = kReduceThreads * sizeof(Pt);
   const int tok_br = prof_begin(PROF_MSM_BUCKET_REDUCE, t);
-  k_msm_wsum_level<F><<<(pl.bwin * ngroups + 63) / 64, 64, 0, t>>>(buckets, pl.nb, pl.group, 1u, (uint32_t)pl.bwin, ngroups,
-                                                                  groups, runs0);
-  {
-    const Pt* in = runs0;
-    uint32_t in_cnt = ngroups;
-    for (int l = 0; l < lv.n; l++) {
-      Pt* acc_l = upper + lv.acc_off[l];
-      Pt* run_l = acc_l + (uint64_t)pl.bwin * lv.cnt[l];
-      k_msm_wsum_level<F><<<(pl.bwin * lv.cnt[l] + 63) / 64, 64, 0, t>>>(in, in_cnt, 1u << kWsumUpperLogG, 0u, (uint32_t)pl.bwin,
-                                                                        lv.cnt[l], acc_l, run_l);
-      in = run_l;
-      in_cnt = lv.cnt[l];
-    }
+  k_msm_wsum_level0<F><<<(unsigned)((arr_pts + 63) / 64), 64, 0, t>>>(buckets, pl.nb, pl.group, (uint32_t)pl.bwin, ngroups,
+                                                                       groups, ping);
+  int rounds = 0;
+  for (uint32_t d = 1; d < ngroups; d <<= 1) {
+    k_msm_suffix_round<F><<<(unsigned)((arr_pts + 127) / 128), 128, 0, t>>>(ping, pong, ngroups, d, (uint32_t)arr_pts);
+    std::swap(ping, pong);
+    rounds++;
   }
   prof_end(tok_br, t);
   const int tok_sums = prof_begin(PROF_MSM_SUMS, t);
+  const uint32_t narr2 = 2u * pl.bwin;
   if (two_level) {
-    k_msm_slice_sum<F><<<pl.bwin * kSlices, kReduceThreads, red_smem, t>>>(groups, ngroups / kSlices, mids);
-    k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, t>>>(mids, kSlices, windows);
+    k_msm_range_sum<F><<<dim3(kSlices, narr2), kReduceThreads, red_smem, t>>>(groups, ping, (uint32_t)pl.bwin, ngroups,
+                                                                             (ngroups + kSlices - 1) / kSlices, mids);
+    k_msm_range_sum<F><<<dim3(1, narr2), kReduceThreads, red_smem, t>>>(mids, mids, narr2, kSlices, kSlices, sums);
   } else {
-    k_msm_slice_sum<F><<<pl.bwin, kReduceThreads, red_smem, t>>>(groups, ngroups, windows);
+    k_msm_range_sum<F><<<dim3(1, narr2), kReduceThreads, red_smem, t>>>(groups, ping, (uint32_t)pl.bwin, ngroups, ngroups, sums);
   }
   int log_g0 = 0;
   while ((1u << log_g0) < pl.group) log_g0++;
-  if (lv.n) k_msm_wsum_finish<F><<<pl.bwin, kReduceThreads, red_smem, t>>>(upper, lv, (uint32_t)log_g0, windows);
+  k_msm_wsum_combine<F><<<(pl.bwin + 31) / 32, 32, 0, t>>>(sums, (uint32_t)pl.bwin, (uint32_t)log_g0, windows);
   k_msm_horner<F><<<1, 128, 0, t>>>(windows, pl, (Pt*)d_out);
   prof_end(tok_sums, t);
   // join: the caller's stream waits for the tail; otherwise the result is ready when ws.e_back fires
   // (ws.wait_tail(other_stream)) and the caller's stream may run ahead with independent bulk work
   ws.hop_back(s, join);
-  prof_count_launches((two_level ? 16 : 15) + lv.n + (lv.n ? 1 : 0));
+  prof_count_launches((two_level ? 17 : 16) + rounds);
   B200_CUDA(cudaGetLastError());
 }
 
@@ -746,6 +730,20 @@ struct CurveImpl : CurveBackend {
     // 3. (a*b - c) / (g^n - 1) fused into the load of the inverse coset transform; g^-i / n on store
     NttScale ci{SCALE_POW_BITREV, d.lo_bits, d.gi_lo.p, d.gi_hi_scaled.p, nullptr};
     run_passes<false>(d.logn, v[0], twi, none, ci, v[1], v[2], consts + 3, s);
+  }
+
+  void coset_evals(NttDomain& d, void* d_v, cudaStream_t s) override {
+    const NttScale none{SCALE_NONE, 0, nullptr, nullptr, nullptr};
+    run_passes<false>(d.logn, (FrEl*)d_v, (const FrEl*)d.tw_inv.p, none, none, nullptr, nullptr, nullptr, s);
+    NttScale cs{SCALE_POW_BITREV, d.lo_bits, d.g_lo.p, d.g_hi_scaled.p, nullptr};
+    run_passes<true>(d.logn, (FrEl*)d_v, (const FrEl*)d.tw_fwd.p, cs, none, nullptr, nullptr, nullptr, s);
+  }
+
+  void compute_h_tail(NttDomain& d, void* d_a, void* d_b, void* d_c, cudaStream_t s) override {
+    const FrEl* consts = (const FrEl*)d.consts.p;
+    const NttScale none{SCALE_NONE, 0, nullptr, nullptr, nullptr};
+    NttScale ci{SCALE_POW_BITREV, d.lo_bits, d.gi_lo.p, d.gi_hi_scaled.p, nullptr};
+    run_passes<false>(d.logn, (FrEl*)d_a, (const FrEl*)d.tw_inv.p, none, ci, (const FrEl*)d_b, (const FrEl*)d_c, consts + 3, s);
   }
 
   void g1_decompress(const void* d_bytes, void* d_affine, uint32_t n, uint32_t* d_err, cudaStream_t s) override {

@@ -703,49 +703,59 @@ k_msm_ovf_merge_l2(const OvfBucket* __restrict__ obuckets, const OvfCounters* __
 }
 
 // ------------------------------------------------------------------------------------ bucket reduction
-// sum_k (k + 1) B_k by hierarchical running sums - two full additions per bucket and nothing else.
+// sum_k (k + 1) B_k with two full additions per bucket and a log-depth tail.
 //
 // Level 0 cuts the nb buckets of an array into groups of G0; thread (w, g) walks its group from the top with the
-// classic running sum and emits  acc = sum_j (j + 1) B[g G0 + j]  and  run = sum_j B[g G0 + j].  Then
-//     sum_k (k + 1) B_k = S_0 + G0 * sum_g g run_g ,      S_0 = sum_g acc_g
-// and the weighted sum over the groups' `run` values is the same problem again (weights g instead of g + 1, groups
-// of G1 = 16): level l emits acc_l / run_l from run_(l-1) until one group is left.  With T_L = S_L and
-// T_l = S_l + G_l T_(l+1) the window sum is T_0.  (Round 1 multiplied every group's run by its base with a 32-step
-// double-and-add: +57% multiplier work on top of the two additions per bucket.)
-//
-// in: `narrays` arrays of `count` points, array a at in + a * count.  off = 1 at level 0, 0 above.
+// classic running sum and emits  acc_g = sum_j (j + 1) B[g G0 + j]  and  run_g = sum_j B[g G0 + j].  Then
+//     sum_k (k + 1) B_k = sum_g acc_g + G0 * sum_g g run_g .
+// The weighted sum over the (<= 2^14) run values is taken WITHOUT another serial pass: run_g is stored one slot to
+// the left (slot g - 1), a Hillis-Steele suffix scan (log2(ng) rounds of one addition per element, k_msm_suffix_round)
+// turns slot i into sum_{g > i} run_g, and the plain sum of all slots is sum_g g run_g.  Both plain sums run through the
+// block-tree reduction (k_msm_range_sum).  Dependent-addition depth: 2 G0 (level 0) + log2(ng) + ~15, instead of the
+// 2 G0 + 32-step double-and-add per group of round 1 - and the multiplier work drops by a third.
 template <class F>
 __global__ void __launch_bounds__(64)
-k_msm_wsum_level(const XYZZ<F>* __restrict__ in, uint32_t count, uint32_t G, uint32_t off, uint32_t narrays,
-                 uint32_t ngroups, XYZZ<F>* __restrict__ acc_out, XYZZ<F>* __restrict__ run_out) {
+k_msm_wsum_level0(const XYZZ<F>* __restrict__ buckets, uint32_t nb, uint32_t G, uint32_t narrays, uint32_t ngroups,
+                  XYZZ<F>* __restrict__ acc_out, XYZZ<F>* __restrict__ run_shifted) {
   using E = EC<F>;
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= narrays * ngroups) return;
   uint32_t w = t / ngroups, g = t % ngroups;
-  const XYZZ<F>* X = in + (uint64_t)w * count;
-  const uint32_t first = g * G;
+  const XYZZ<F>* X = buckets + (uint64_t)w * nb + (uint64_t)g * G;
   XYZZ<F> run, acc;
   E::set_inf(run);
   E::set_inf(acc);
   for (int j = (int)G - 1; j >= 0; j--) {
-    if (first + (uint32_t)j < count) {
-      XYZZ<F> b;
-      load16_rw(b, X + first + j);
-      E::add(run, b);
-    }
-    if ((uint32_t)j + off) E::add(acc, run);
+    XYZZ<F> b;
+    load16_rw(b, X + j);
+    E::add(run, b);
+    E::add(acc, run);
   }
   store16(acc_out + t, acc);
-  store16(run_out + t, run);
+  if (g) store16(run_shifted + t - 1, run);
+  if (g == ngroups - 1) {
+    E::set_inf(run);
+    store16(run_shifted + t, run);   // the last slot of every array: nothing lies to its right
+  }
 }
 
-constexpr int kWsumMaxLevels = 8;
-constexpr uint32_t kWsumUpperLogG = 4;   // groups of 16 above level 0: short dependent chains, the data is tiny
-struct WsumLevels {
-  int n;                               // levels above level 0
-  uint32_t acc_off[kWsumMaxLevels];    // offset of level l's acc array inside `upper` (points)
-  uint32_t cnt[kWsumMaxLevels];        // groups per bucket array at level l
-};
+// one round of the suffix scan: out[i] = in[i] + in[i + d] (inside each array of n elements)
+template <class F>
+__global__ void __launch_bounds__(128)
+k_msm_suffix_round(const XYZZ<F>* __restrict__ in, XYZZ<F>* __restrict__ out, uint32_t n, uint32_t d, uint32_t total) {
+  using E = EC<F>;
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t i = t % n;
+  XYZZ<F> a;
+  load16_rw(a, in + t);
+  if (i + d < n) {
+    XYZZ<F> b;
+    load16_rw(b, in + t + d);
+    E::add(a, b);
+  }
+  store16(out + t, a);
+}
 
 // block b: out[b] = sum of in[b * per_slice .. (b + 1) * per_slice)   (window sums, in one or two levels)
 template <class F>
@@ -766,40 +776,43 @@ k_msm_slice_sum(const XYZZ<F>* __restrict__ in, uint32_t per_slice, XYZZ<F>* __r
   if (threadIdx.x == 0) store16(out + blockIdx.x, acc);
 }
 
-// block w: windows[w] <- S_0 + G0 * (S_1 + 16 * (S_2 + 16 * ( ... S_L)))   with S_0 already in windows[w] and
-// S_l = sum of level l's acc values of array w
+// block (slice, a): out[a * gridDim.x + slice] = sum of per_slice consecutive elements of array a, where arrays
+// 0 .. split-1 live at base0 + a * n and arrays split .. at base1 + (a - split) * n (elements beyond n are skipped)
 template <class F>
 __global__ void __launch_bounds__(kReduceThreads)
-k_msm_wsum_finish(const XYZZ<F>* __restrict__ upper, WsumLevels lv, uint32_t logG0, XYZZ<F>* __restrict__ windows) {
+k_msm_range_sum(const XYZZ<F>* __restrict__ base0, const XYZZ<F>* __restrict__ base1, uint32_t split, uint32_t n,
+                uint32_t per_slice, XYZZ<F>* __restrict__ out) {
   extern __shared__ uint4 smem_raw[];
   XYZZ<F>* sm = reinterpret_cast<XYZZ<F>*>(smem_raw);
   using E = EC<F>;
-  const uint32_t w = blockIdx.x;
-  XYZZ<F> T;
-  E::set_inf(T);
-  for (int l = lv.n - 1; l >= 0; l--) {
-    const XYZZ<F>* A = upper + lv.acc_off[l] + (uint64_t)w * lv.cnt[l];
-    XYZZ<F> s;
-    E::set_inf(s);
-    for (uint32_t g = threadIdx.x; g < lv.cnt[l]; g += kReduceThreads) {
-      XYZZ<F> p;
-      load16_rw(p, A + g);
-      E::add(s, p);
-    }
-    block_sum<F, kReduceThreads>(s, sm);
-    if (threadIdx.x == 0) {
-      for (uint32_t k = 0; k < kWsumUpperLogG; k++) E::dbl(T);
-      E::add(T, s);
-    }
-    __syncthreads();
+  const uint32_t a = blockIdx.y;
+  const XYZZ<F>* A = a < split ? base0 + (uint64_t)a * n : base1 + (uint64_t)(a - split) * n;
+  const uint32_t lo = blockIdx.x * per_slice;
+  const uint32_t hi = lo + per_slice < n ? lo + per_slice : n;
+  XYZZ<F> acc;
+  E::set_inf(acc);
+  for (uint32_t g = lo + threadIdx.x; g < hi; g += kReduceThreads) {
+    XYZZ<F> p;
+    load16_rw(p, A + g);
+    E::add(acc, p);
   }
-  if (threadIdx.x == 0) {
-    for (uint32_t k = 0; k < logG0; k++) E::dbl(T);
-    XYZZ<F> s0;
-    load16_rw(s0, windows + w);
-    E::add(T, s0);
-    store16(windows + w, T);
-  }
+  block_sum<F, kReduceThreads>(acc, sm);
+  if (threadIdx.x == 0) store16(out + (uint64_t)a * gridDim.x + blockIdx.x, acc);
+}
+
+// thread w: windows[w] = sums[w] + 2^logG0 * sums[narr + w]   (sum acc_g + G0 * sum g run_g)
+template <class F>
+__global__ void k_msm_wsum_combine(const XYZZ<F>* __restrict__ sums, uint32_t narr, uint32_t logG0,
+                                   XYZZ<F>* __restrict__ windows) {
+  using E = EC<F>;
+  uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= narr) return;
+  XYZZ<F> T, s0;
+  load16_rw(T, sums + narr + w);
+  for (uint32_t k = 0; k < logG0; k++) E::dbl(T);
+  load16_rw(s0, sums + w);
+  E::add(T, s0);
+  store16(windows + w, T);
 }
 
 // windowed mode: out[0] = sum_w 2^(c w) windows[w]  (single thread; latency hidden by the other MSM streams)

@@ -291,6 +291,8 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
   if (in.wires.len != m) throw std::runtime_error("wires: expected nb_wires elements");
   if (in.a.len > n || in.b.len != in.a.len || in.c.len != in.a.len)
     throw std::runtime_error("a/b/c: need equal lengths <= domain size");
+  if (in.abc_form > 1) throw std::runtime_error("abc_form must be 0 or 1");
+  if (in.abc_form == 1 && in.a.len != n) throw std::runtime_error("abc_form = 1 needs domain_size coset evaluations");
   if (in.nb_commitments != commit_n.size()) throw std::runtime_error("nb_commitments mismatch with proving key");
   if (!in.r || !in.s) throw std::runtime_error("r / s missing");
   if ((m && !in.wires.ptr) || (in.a.len && (!in.a.ptr || !in.b.ptr || !in.c.ptr)))
@@ -397,7 +399,8 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
 
   // ---- quotient, Z MSM, proof of knowledge
   B200_CUDA(cudaStreamWaitEvent(sb, S.ev[1], 0));
-  cb->compute_h(I.dom, a, b, c, sb);
+  if (in.abc_form == 1) cb->compute_h_tail(I.dom, a, b, c, sb);
+  else cb->compute_h(I.dom, a, b, c, sb);
   cb->msm(1, nullptr, a + z_offset * frb, nZ, o_z, S.ws[0], sb, 0, nullptr, nullptr, &I.tZ, false);
   if (have_pok) {
     // segment i of the committed values is scaled by challenge^i: scale every later segment once per step

@@ -105,7 +105,8 @@ def slice_proving_key(pk, ccs, world, rank):
                                L=[], R=[], O=[], commitments=[{"private_committed": local_skip, "commitment_index": None}]
                                if local_skip else [])
     sub_ccs.krs_skip_wires = lambda: set(local_skip)
-    return sub, sub_ccs, {"wire_range": (wlo, whi), "z_offset": zlo, "first": first}
+    return sub, sub_ccs, {"wire_range": (wlo, whi), "z_offset": zlo, "first": first,
+                          "domain_size": int(pk.domain_cardinality)}
 
 
 def register_key_slice(sub_pk, sub_ccs, info):
@@ -114,7 +115,17 @@ def register_key_slice(sub_pk, sub_ccs, info):
     return prover.register_proving_key(sub_pk, sub_ccs, z_offset=info["z_offset"])
 
 
-def prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_committed_dev=None, fold_challenge=None):
+def coset_evals_inplace(handle, buf):
+    """buf (domain_size fr, natural order, zero padded, on the current device) <- its evaluations on the coset
+    g<omega>: the per-vector half of the quotient (b200_pk_coset_evals_dev), enqueued on the current torch stream."""
+    import torch
+    from . import capi
+    capi.check(capi.lib.b200_pk_coset_evals_dev(handle, buf.data_ptr(), torch.cuda.current_device(),
+                                                torch.cuda.current_stream().cuda_stream))
+
+
+def prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_committed_dev=None, fold_challenge=None,
+                  abc_form=0):
     """Partial sums of one key slice: W_dev is the FULL wire vector on this device (the slice is taken
     here), a/b/c are full.  Returns a device tensor of 5*xyzz(1)+xyzz(2) bytes whose K slot already holds
     K_g + s*Ar_g + r*Bs1_g.  fold_challenge (int) is required with more than one commitment.
@@ -139,6 +150,7 @@ def prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_co
         pcs[i] = capi.Slice(t.data_ptr(), cnt)
     pin.priv_committed = pcs
     pin.fold_challenge = None
+    pin.abc_form = abc_form
     if k > 1:
         if fold_challenge is None:
             raise ValueError("fold_challenge is required with more than one commitment")
@@ -164,11 +176,38 @@ def assemble(L, partials_dev, nparts, r, s, have_pok):
     return {"Ar": buf[:g1b], "Krs": buf[g1b:2 * g1b], "CommitmentPok": buf[2 * g1b:3 * g1b], "Bs": buf[3 * g1b:]}
 
 
+def quotient_owners(world):
+    """Which rank transforms a, b, c when the quotient is sharded (two transforms per vector)."""
+    return (0, 1 % world, 2 % world) if world >= 3 else (0, 1 % world, 0)
+
+
 def prove_range_split(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, have_pok, priv_committed_dev=None,
-                      group=None, fold_challenge=None):
+                      group=None, fold_challenge=None, shard_quotient=True):
     """One proof over all ranks of `group`: partial sums on every GPU, all-gather (NCCL / NVLink), local
-    assembly.  Every rank returns the same proof."""
+    assembly.  Every rank returns the same proof.
+
+    shard_quotient: instead of every GPU computing the whole quotient (7 transforms), the owner of each of a, b, c
+    turns it into coset evaluations (2 transforms) and broadcasts them over NVLink (domain_size * fr_bytes each);
+    every GPU then runs only the pointwise division and the last inverse transform."""
+    import torch
     import torch.distributed as dist
-    part = prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_committed_dev, fold_challenge)
+    world = dist.get_world_size(group)
+    if shard_quotient and world > 1:
+        rank = dist.get_rank(group)
+        n = info["domain_size"]
+        frb = L.fr_bytes
+        bufs = info.setdefault("_qbuf", [torch.empty(n * frb, dtype=torch.uint8, device="cuda") for _ in range(3)])
+        owners = quotient_owners(world)
+        for buf, src_vec, owner in zip(bufs, (a_dev, b_dev, c_dev), owners):
+            if rank == owner:
+                buf[:nc * frb].copy_(src_vec[:nc * frb])
+                buf[nc * frb:].zero_()
+                coset_evals_inplace(handle, buf)
+        for buf, owner in zip(bufs, owners):
+            dist.broadcast(buf, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+        part = prove_partial(handle, L, info, W_dev, bufs[0], bufs[1], bufs[2], n, r, s, priv_committed_dev, fold_challenge,
+                             abc_form=1)
+    else:
+        part = prove_partial(handle, L, info, W_dev, a_dev, b_dev, c_dev, nc, r, s, priv_committed_dev, fold_challenge)
     allp = gather_partials(part, group)
-    return assemble(L, allp, dist.get_world_size(group), r, s, have_pok)
+    return assemble(L, allp, world, r, s, have_pok)

@@ -141,6 +141,10 @@ typedef struct {
   uint32_t nb_commitments;
   const b200_slice* priv_committed;   /* privateCommittedValues[i] */
   const void* fold_challenge;     /* fr; only read when nb_commitments > 1 */
+  uint32_t abc_form;              /* 0: a, b, c are the solver's constraint values (the usual case).
+                                     1: a, b, c are already their evaluations on the coset g<omega>, domain_size
+                                        elements each (b200_pk_coset_evals_dev): range-split proving shards the
+                                        quotient - each GPU transforms one vector and broadcasts it over NVLink */
 } b200_prove_in;
 
 typedef struct {
@@ -181,6 +185,11 @@ B200_API int b200_prove_dev(uint64_t handle, const b200_prove_in* in, const b200
  * Device inputs of every `_dev` prove entry point are read on the library's own streams: they must be complete
  * (producer stream synchronised) before the call. */
 B200_API int b200_prove_partial_dev(uint64_t handle, const b200_prove_in* in, void* d_partials_out, int device);
+/* First half of gnark's computeH for ONE vector: d_vec (domain_size fr on the key's device, natural
+ * order, zero padded) <- its evaluations on the coset g<omega> (FFTInverse DIF, then FFT DIT OnCoset), asynchronously on
+ * cuda_stream.  With the three vectors transformed (on three different GPUs and broadcast), b200_prove*_dev with
+ * abc_form = 1 runs only the pointwise division and the last inverse transform. */
+B200_API int b200_pk_coset_evals_dev(uint64_t handle, void* d_vec, int device, void* cuda_stream);
 B200_API int b200_assemble_dev(int curve, const void* d_partials, uint32_t nparts, const void* d_r, const void* d_s,
                                int have_pok, void* d_out, void* cuda_stream);
 

@@ -181,3 +181,105 @@ def compute_cell_proofs(blob: bytes, monomial_points, cells=None):
         q = cell_quotient(coeffs, k)
         out[k] = g1_compress(cx.G1.msm(monomial_points[:len(q)], q))
     return out
+
+
+# ----------------------------------------------------------------------------- pairing-based verification
+# The reference verifies openings in-circuit against the ceremony's [tau]_2 (/root/reference/crypto/blobs/kzg.go:26-45,
+# evaluation.go) and geth verifies them natively (kzg4844.VerifyProof / VerifyCellProofBatch); both are the check
+#     e(C - [y]_1, G_2) = e(pi, [tau]_2 - [z]_2)          (cells: e(C - [I_k(tau)]_1, G_2) = e(pi_k, [tau^64]_2 - [a_k]_2))
+# against reference-held material only - this pins every opening / cell proof the GPU or this oracle produces.
+def g2_decompress(b: bytes):
+    """96-byte compressed BLS12-381 G2 point (ZCash / gnark-crypto encoding: x.c1 first, flags in the top 3 bits)."""
+    cx = C.ctx("bls12_381")
+    p = cx.p
+    assert len(b) == 96 and b[0] & FLAG_COMPRESSED
+    if b[0] & FLAG_INFINITY:
+        return None
+    x1 = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:48], "big")
+    x0 = int.from_bytes(b[48:], "big")
+    F2 = cx.F2
+    x = (x0, x1)
+    y = F2.sqrt(F2.add(F2.mul(F2.sqr(x), x), cx.G2.b))
+    assert y is not None, "x not on the twist"
+    largest = (y[1] > (p - 1) // 2) if y[1] else (y[0] > (p - 1) // 2)     # lexicographic: c1 first
+    if largest != bool(b[0] & FLAG_LARGEST):
+        y = F2.neg(y)
+    return (x, y)
+
+
+def verify_kzg_proof(commitment: bytes, z: int, y: int, proof: bytes, tau_g2, g2_gen=None) -> bool:
+    """e(C - [y]_1, G_2) * e(-pi, [tau]_2 - [z]_2) == 1  (EIP-4844 verify_kzg_proof_impl)."""
+    from . import pairing
+    pr = pairing.get("bls12_381")
+    cx = pr.cx
+    r = cx.r
+    G1, G2 = cx.G1, cx.G2
+    g2 = g2_gen or cx_g2_generator()
+    Cm, Pi = g1_decompress(commitment), g1_decompress(proof)
+    lhs = G1.add(Cm, G1.neg(G1.mul(cx.g1, y % r)))
+    rhs = G2.add(tau_g2, G2.neg(G2.mul(g2, z % r)))
+    return pr.product_is_one([(lhs, g2), (G1.neg(Pi), rhs)])
+
+
+def cx_g2_generator():
+    """The ceremony's G_2 = the standard BLS12-381 G2 generator (kzg.go:33-38; equals [tau^0]_2 of the SRS file)."""
+    return g2_decompress(bytes.fromhex(
+        "93e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e"
+        "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8"))
+
+
+def extended_cell_values(blob: bytes, k: int):
+    """The 64 evaluations that make cell k of the extended blob (cells < 64 are the blob's own chunks)."""
+    r = P.BLS12_381.r
+    vals = blob_scalars(blob)
+    m = FIELD_ELEMENTS_PER_CELL
+    if k < len(vals) // m:
+        return vals[m * k:m * (k + 1)]
+    coeffs = blob_coefficients(vals)
+    n = len(vals)
+    logext = (2 * n).bit_length() - 1
+    w = pow(PRIMITIVE_ROOT_2_32, 1 << (32 - logext), r)
+    out = []
+    for j in range(m):
+        x = pow(w, N.bitrev(m * k + j, logext), r)
+        acc = 0
+        for cf in reversed(coeffs):
+            acc = (acc * x + cf) % r
+        out.append(acc)
+    return out
+
+
+def cell_interpolant(cell_vals, k, n=4096):
+    """Coefficients (degree < 64) of the polynomial through cell k's points x_j = h_k zeta^brp6(j)."""
+    r = P.BLS12_381.r
+    m = FIELD_ELEMENTS_PER_CELL
+    logm = m.bit_length() - 1
+    h = cell_coset_shift(k, n)
+    zeta = pow(PRIMITIVE_ROOT_2_32, 1 << (32 - logm), r)
+    zinv = pow(zeta, -1, r)
+    minv = pow(m, -1, r)
+    hinv = pow(h, -1, r)
+    coeffs = []
+    for i in range(m):
+        acc = 0
+        for j, v in enumerate(cell_vals):
+            acc += v * pow(zinv, i * N.bitrev(j, logm) % m, r)
+        coeffs.append(acc % r * minv % r * pow(hinv, i, r) % r)
+    return coeffs
+
+
+def verify_cell_proof(commitment: bytes, k: int, cell_vals, proof: bytes, mono_g1_64, tau64_g2, n=4096) -> bool:
+    """e(C - [I_k(tau)]_1, G_2) * e(-pi_k, [tau^64]_2 - [h_k^64]_2) == 1  (EIP-7594 verify_cell_kzg_proof)."""
+    from . import pairing
+    pr = pairing.get("bls12_381")
+    cx = pr.cx
+    r = cx.r
+    G1, G2 = cx.G1, cx.G2
+    g2 = cx_g2_generator()
+    coeffs = cell_interpolant(cell_vals, k, n)
+    interp = G1.msm_naive(mono_g1_64, coeffs)
+    Cm, Pi = g1_decompress(commitment), g1_decompress(proof)
+    lhs = G1.add(Cm, G1.neg(interp))
+    a = pow(cell_coset_shift(k, n), FIELD_ELEMENTS_PER_CELL, r)
+    rhs = G2.add(tau64_g2, G2.neg(G2.mul(g2, a)))
+    return pr.product_is_one([(lhs, g2), (G1.neg(Pi), rhs)])

@@ -63,6 +63,9 @@ def _worker(rank, world, port, q):
     out["prove_split"] = (L.dec_affine(got["Ar"], 1)[0] == want["Ar"] and L.dec_affine(got["Bs"], 2)[0] == want["Bs"]
                           and L.dec_affine(got["Krs"], 1)[0] == want["Krs"]
                           and L.dec_affine(got["CommitmentPok"], 1)[0] == want["CommitmentPok"])
+    # the unsharded quotient (every GPU computes the whole of it) must give the same bytes
+    got_u = multi.prove_range_split(h, L, info, Wd, ad, bd, cd, len(a), r, s, True, pc, shard_quotient=False)
+    out["prove_split_unsharded_quotient"] = all(np.array_equal(got_u[k], got[k]) for k in ("Ar", "Bs", "Krs", "CommitmentPok"))
     prover.release_proving_key(sub)
     q.put((rank, out))
     dist.destroy_process_group()

@@ -202,18 +202,31 @@ def test_range_split_prove_single_gpu(env, cname, parts):
     Wd, ad, bd, cd = dev(W), dev(a), dev(b), dev(c)
     committed = cs.commitments[0]["private_committed"]
     pc = [(dev([W[i] for i in committed]), len(committed))]
-    partials, subs = [], []
+    partials, subs, handles, infos = [], [], [], []
     try:
         for rank in range(parts):
             sub, sub_ccs, info = multi.slice_proving_key(pk, ccs, parts, rank)
             h = multi.register_key_slice(sub, sub_ccs, info)
             subs.append(sub)
+            handles.append(h)
+            infos.append(info)
             partials.append(multi.prove_partial(h, L, info, Wd, ad, bd, cd, len(a), r, s, pc))
         got = multi.assemble(L, torch.cat(partials), parts, r, s, have_pok=True)
         assert L.dec_affine(got["Ar"], 1)[0] == want["Ar"]
         assert L.dec_affine(got["Bs"], 2)[0] == want["Bs"]
         assert L.dec_affine(got["Krs"], 1)[0] == want["Krs"]
         assert L.dec_affine(got["CommitmentPok"], 1)[0] == want["CommitmentPok"]
+        # sharded quotient: a, b, c arrive as coset evaluations (b200_pk_coset_evals_dev, abc_form = 1) - same proof
+        n = pk.domain_cardinality
+        pad = lambda v: torch.cat([v, torch.zeros((n - len(a)) * L.fr_bytes, dtype=torch.uint8, device="cuda")])
+        ea, eb, ec = pad(ad), pad(bd), pad(cd)
+        for v in (ea, eb, ec):
+            multi.coset_evals_inplace(handles[0], v)
+        partials2 = [multi.prove_partial(h, L, info, Wd, ea, eb, ec, n, r, s, pc, abc_form=1)
+                     for h, info in zip(handles, infos)]
+        got2 = multi.assemble(L, torch.cat(partials2), parts, r, s, have_pok=True)
+        for key in ("Ar", "Bs", "Krs", "CommitmentPok"):
+            assert np.array_equal(got2[key], got[key]), key
     finally:
         for sub in subs:
             prover.release_proving_key(sub)
