@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(64) k_build_tables(const Affine<F>* __restrict
     xy.y = x.y;
     store16(tables + (uint64_t)j * npts + i, xy);
     El d;
+    F::mul(d, x.zz, x.zzz);
     if (EC<F>::is_inf(x)) F::set_one(d);   // infinity (or a point of 2-power order): keeps the product invertible
-    else F::mul(d, x.zz, x.zzz);
     store16(sc + 0, x.zz);
     store16(sc + 1, x.zzz);
     store16(sc + 2, run);                  // product of d_1 .. d_{j-1}

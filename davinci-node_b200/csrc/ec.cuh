@@ -93,81 +93,96 @@ struct EC {
     F::mul(p.zzz, w, p.zzz);
   }
 
+  // Control-flow rule for everything below: an out-of-line call (dbl, dbl_affine, the Fp2 products) never sits in a
+  // branch whose sibling threads keep executing other code of the same function.  ptxas keeps warp-uniform values
+  // (stack addresses, the Montgomery constant) in per-WARP uniform registers; a callee entered by a divergent subset
+  // overwrites them under the feet of the threads still running the caller's main path (found with compute-sanitizer:
+  // add() -> dbl() loaded M0 into the UR holding add()'s frame pointer).  So the special cases are classified first,
+  // the generic path runs under a plain `if`, and the rare doubling call comes last, where every other thread of the
+  // warp waits at the reconvergence point.
+  enum : int { kModeSkip = 0, kModeCopy = 1, kModeGeneric = 2, kModeDouble = 3, kModeCancel = 4 };
+
   // acc += (affine p)           (madd-2008-s), all special cases handled
   static __device__ __forceinline__ void madd(Pt& acc, const Aff& p) {
-    if (is_inf(p)) return;
-    if (is_inf(acc)) {
+    El u2, s2;
+    int mode;
+    if (is_inf(p)) {
+      mode = kModeSkip;
+    } else if (is_inf(acc)) {
+      mode = kModeCopy;
+    } else {
+      F::mul(u2, p.x, acc.zz);
+      F::mul(s2, p.y, acc.zzz);
+      F::sub(u2, u2, acc.x);     // P
+      F::sub(s2, s2, acc.y);     // R
+      mode = !F::is_zero(u2) ? kModeGeneric : (F::is_zero(s2) ? kModeDouble : kModeCancel);
+    }
+    if (mode == kModeGeneric) {
+      El pp, ppp, q, t;
+      F::sqr(pp, u2);
+      F::mul(ppp, u2, pp);
+      F::mul(q, acc.x, pp);
+      F::sqr(t, s2);
+      F::sub(t, t, ppp);
+      F::sub(t, t, q);
+      F::sub(acc.x, t, q);       // X3 = R^2 - PPP - 2Q
+      F::sub(q, q, acc.x);
+      F::mul(q, s2, q);          // R (Q - X3)
+      F::mul(t, acc.y, ppp);
+      F::sub(acc.y, q, t);
+      F::mul(acc.zz, acc.zz, pp);
+      F::mul(acc.zzz, acc.zzz, ppp);
+    } else if (mode == kModeCopy) {
       acc.x = p.x;
       acc.y = p.y;
       F::set_one(acc.zz);
       F::set_one(acc.zzz);
-      return;
+    } else if (mode == kModeCancel) {
+      set_inf(acc);
     }
-    El u2, s2, pp, ppp, q, t;
-    F::mul(u2, p.x, acc.zz);
-    F::mul(s2, p.y, acc.zzz);
-    F::sub(u2, u2, acc.x);     // P
-    F::sub(s2, s2, acc.y);     // R
-    if (F::is_zero(u2)) {
-      if (F::is_zero(s2)) {
-        dbl_affine(acc, p);
-      } else {
-        set_inf(acc);
-      }
-      return;
-    }
-    F::sqr(pp, u2);
-    F::mul(ppp, u2, pp);
-    F::mul(q, acc.x, pp);
-    F::sqr(t, s2);
-    F::sub(t, t, ppp);
-    F::sub(t, t, q);
-    F::sub(acc.x, t, q);       // X3 = R^2 - PPP - 2Q
-    F::sub(q, q, acc.x);
-    F::mul(q, s2, q);          // R (Q - X3)
-    F::mul(t, acc.y, ppp);
-    F::sub(acc.y, q, t);
-    F::mul(acc.zz, acc.zz, pp);
-    F::mul(acc.zzz, acc.zzz, ppp);
+    if (mode == kModeDouble) dbl_affine(acc, p);
   }
 
   // acc += b                    (add-2008-s), all special cases handled
   static __device__ __noinline__ void add(Pt& acc, const Pt& b) {
-    if (is_inf(b)) return;
-    if (is_inf(acc)) {
+    El u1, u2, s1, s2;
+    int mode;
+    if (is_inf(b)) {
+      mode = kModeSkip;
+    } else if (is_inf(acc)) {
+      mode = kModeCopy;
+    } else {
+      F::mul(u1, acc.x, b.zz);
+      F::mul(u2, b.x, acc.zz);
+      F::mul(s1, acc.y, b.zzz);
+      F::mul(s2, b.y, acc.zzz);
+      F::sub(u2, u2, u1);        // P
+      F::sub(s2, s2, s1);        // R
+      mode = !F::is_zero(u2) ? kModeGeneric : (F::is_zero(s2) ? kModeDouble : kModeCancel);
+    }
+    if (mode == kModeGeneric) {
+      El pp, ppp, q, t;
+      F::sqr(pp, u2);
+      F::mul(ppp, u2, pp);
+      F::mul(q, u1, pp);
+      F::sqr(t, s2);
+      F::sub(t, t, ppp);
+      F::sub(t, t, q);
+      F::sub(acc.x, t, q);
+      F::sub(q, q, acc.x);
+      F::mul(q, s2, q);
+      F::mul(t, s1, ppp);
+      F::sub(acc.y, q, t);
+      F::mul(acc.zz, acc.zz, b.zz);
+      F::mul(acc.zz, acc.zz, pp);
+      F::mul(acc.zzz, acc.zzz, b.zzz);
+      F::mul(acc.zzz, acc.zzz, ppp);
+    } else if (mode == kModeCopy) {
       acc = b;
-      return;
+    } else if (mode == kModeCancel) {
+      set_inf(acc);
     }
-    El u1, u2, s1, s2, pp, ppp, q, t;
-    F::mul(u1, acc.x, b.zz);
-    F::mul(u2, b.x, acc.zz);
-    F::mul(s1, acc.y, b.zzz);
-    F::mul(s2, b.y, acc.zzz);
-    F::sub(u2, u2, u1);        // P
-    F::sub(s2, s2, s1);        // R
-    if (F::is_zero(u2)) {
-      if (F::is_zero(s2)) {
-        dbl(acc);
-      } else {
-        set_inf(acc);
-      }
-      return;
-    }
-    F::sqr(pp, u2);
-    F::mul(ppp, u2, pp);
-    F::mul(q, u1, pp);
-    F::sqr(t, s2);
-    F::sub(t, t, ppp);
-    F::sub(t, t, q);
-    F::sub(acc.x, t, q);
-    F::sub(q, q, acc.x);
-    F::mul(q, s2, q);
-    F::mul(t, s1, ppp);
-    F::sub(acc.y, q, t);
-    F::mul(acc.zz, acc.zz, b.zz);
-    F::mul(acc.zz, acc.zz, pp);
-    F::mul(acc.zzz, acc.zzz, b.zzz);
-    F::mul(acc.zzz, acc.zzz, ppp);
+    if (mode == kModeDouble) dbl(acc);
   }
 
   // r = [k] p for a small unsigned k (double-and-add, MSB first)

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace b200 {
 
@@ -42,8 +43,70 @@ void sync_bulk(PkSlot& S) {
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------ HostStager
+void HostStager::init(int dev) {
+  device = dev;
+  if (pinned) return;
+  B200_CUDA(cudaHostAlloc((void**)&pinned, (size_t)kThreads * kRing * kChunk, cudaHostAllocPortable));
+  for (auto& row : ev)
+    for (auto& e : row) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+
+HostStager::~HostStager() {
+  if (pinned) cudaFreeHost(pinned);
+  for (auto& row : ev)
+    for (auto& e : row)
+      if (e) cudaEventDestroy(e);
+}
+
+void HostStager::copy(void* d_dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+  if (!bytes) return;
+  static const bool enabled = [] {
+    const char* e = std::getenv("B200_STAGER");
+    return !(e && std::atoi(e) == 0);
+  }();
+  bool pageable = false;
+  if (enabled && kind == cudaMemcpyHostToDevice && bytes >= (8u << 20)) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();   // unknown pointer: treat as page-locked, clear the sticky-free error
+  }
+  if (!pageable) {
+    B200_CUDA(cudaMemcpyAsync(d_dst, src, bytes, kind, s));
+    return;
+  }
+  init(device);
+  const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+  std::string errs[kThreads];
+  auto worker = [&](int t) {
+    try {
+      B200_CUDA(cudaSetDevice(device));
+      for (size_t c = t, k = 0; c < nchunks; c += kThreads, k++) {
+        const int slot = (int)(k % kRing);
+        uint8_t* stage = pinned + ((size_t)t * kRing + slot) * kChunk;
+        if (k >= (size_t)kRing) B200_CUDA(cudaEventSynchronize(ev[t][slot]));   // its previous DMA has drained
+        const size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+        std::memcpy(stage, (const uint8_t*)src + off, len);
+        B200_CUDA(cudaMemcpyAsync((uint8_t*)d_dst + off, stage, len, cudaMemcpyHostToDevice, s));
+        B200_CUDA(cudaEventRecord(ev[t][slot], s));
+      }
+      // the ring may be reused by the next copy() right away: wait for this thread's last DMAs
+      for (int slot = 0; slot < kRing; slot++) B200_CUDA(cudaEventSynchronize(ev[t][slot]));
+    } catch (const std::exception& e) {
+      errs[t] = e.what();
+    }
+  };
+  std::thread th[kThreads];
+  for (int t = 1; t < kThreads; t++) th[t] = std::thread(worker, t);
+  worker(0);
+  for (int t = 1; t < kThreads; t++) th[t].join();
+  for (auto& e : errs)
+    if (!e.empty()) throw CudaError(e);
+}
+
 // ------------------------------------------------------------------------------------ PkInstance
 PkSlot::PkSlot(int dev) : device(dev) {
+  stager.device = dev;
   DeviceScope ds(dev);
   // st[0] bulk kernels, st[1] input copies, st[2] / st[3] extra bulk streams (B200_BULK_STREAMS=3);
   // `hi` runs the single-thread proof assembly at the highest priority
@@ -328,7 +391,7 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
 
   // ---- inputs (sc): wire vector first so the wire-indexed MSMs can start while a, b, c are still arriving
   int tok_in = prof_begin(PROF_INPUTS, sc);
-  B200_CUDA(cudaMemcpyAsync(W, in.wires.ptr, m * frb, kind, sc));
+  S.stager.copy(W, in.wires.ptr, m * frb, kind, sc);
   uint8_t* rs_in = (uint8_t*)S.rs.p;
   B200_CUDA(cudaMemcpyAsync(rs_in, in.r, frb, kind, sc));
   B200_CUDA(cudaMemcpyAsync(rs_in + frb, in.s, frb, kind, sc));
@@ -343,9 +406,9 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
     B200_CUDA(cudaMemsetAsync(c + nc * frb, 0, (n - nc) * frb, sc));
   }
   if (nc) {
-    B200_CUDA(cudaMemcpyAsync(a, in.a.ptr, nc * frb, kind, sc));
-    B200_CUDA(cudaMemcpyAsync(b, in.b.ptr, nc * frb, kind, sc));
-    B200_CUDA(cudaMemcpyAsync(c, in.c.ptr, nc * frb, kind, sc));
+    S.stager.copy(a, in.a.ptr, nc * frb, kind, sc);
+    S.stager.copy(b, in.b.ptr, nc * frb, kind, sc);
+    S.stager.copy(c, in.c.ptr, nc * frb, kind, sc);
   }
   bool have_pok = total_commit > 0 || !commit_n.empty();
   uint8_t* cv = (uint8_t*)S.cvals.p;

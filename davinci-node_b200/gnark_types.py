@@ -8,11 +8,11 @@ solver (gnark's `r1cs.Solve`, SURVEY.md A.1 step 4 - it stays on the CPU in the 
 unchanged gnark code in a real deployment); here it handles the synthetic single-output-wire circuits
 the tests and the bench use.
 """
-import hashlib
 from dataclasses import dataclass, field
 
 import numpy as np
 
+from . import hash_to_field as H2F
 from .layout import Layout
 
 
@@ -68,14 +68,15 @@ class ConstraintSystem:
             s.add(cm["commitment_index"])
         return s
 
-    def commitment_challenge(self, i, commitment_bytes, L: Layout):
-        """Value of commitment wire i.  gnark hashes the marshalled commitment with the option's
-        hash-to-field; that hash is host code outside this backend, so the
-        mirror uses sha256 reduced mod r as a stand-in with the same data flow."""
-        h = hashlib.sha256(b"b200-bsb22|%d|" % i + bytes(commitment_bytes)).digest()
-        return int.from_bytes(h, "big") % L.r
+    def commitment_challenge(self, i, commitment_bytes, L: Layout, vals, hash_kind="default"):
+        """Value of commitment wire i: gnark's `opt.HashToFieldFn` over Commitment.Marshal() || the public committed
+        values.  hash_kind 'default' = hash_to_field "bsb22-commitment" (RFC 9380 xmd),
+        'solidity' = keccak256 (solidity.WithProverTargetSolidityVerifier)."""
+        pt = L.dec_affine(commitment_bytes, 1)[0]
+        pub = [vals[wire] for wire in self.commitments[i].get("public_committed", [])]
+        return H2F.commitment_challenge(hash_kind, pt, pub, L.r, L.fp_bytes)
 
-    def solve(self, w: Witness, commit_hint=None) -> Solution:
+    def solve(self, w: Witness, commit_hint=None, hash_kind="default") -> Solution:
         L = Layout(self.curve_id)
         q = L.r
         if len(w.public) != self.nb_public - 1 or len(w.secret) != self.nb_secret:
@@ -95,7 +96,7 @@ class ConstraintSystem:
                 raise ValueError("circuit has commitments but no commitment hint was supplied")
             cbytes = commit_hint(i, cv)
             commitments.append(cbytes)
-            vals[cm["commitment_index"]] = self.commitment_challenge(i, cbytes, L)
+            vals[cm["commitment_index"]] = self.commitment_challenge(i, cbytes, L, vals, hash_kind)
 
         def ev(terms):
             acc = 0
@@ -121,8 +122,8 @@ class ConstraintSystem:
             c.append(z)
         fold = 0
         if len(self.commitments) > 1:
-            hh = hashlib.sha256(b"G16-BSB22" + b"".join(bytes(cb) for cb in commitments)).digest()
-            fold = int.from_bytes(hh, "big") % q
+            # pedersen.BatchProve: Fiat-Shamir over the commitment wires' values
+            fold = H2F.fold_challenge([vals[cm["commitment_index"]] for cm in self.commitments], q)
         return Solution(L.enc_fr(vals), L.enc_fr(a), L.enc_fr(b), L.enc_fr(c), priv_committed, commitments, fold, vals)
 
 

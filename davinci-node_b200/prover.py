@@ -111,7 +111,34 @@ def release_proving_key(pk: ProvingKey):
         capi.check(capi.lib.b200_pk_release(ent[1]))
 
 
-def _gpu_prove(curve_id, ccs: ConstraintSystem, pk: ProvingKey, w: Witness, device=-1):
+class ProverOption:
+    """backend.ProverOption mirror: only the option that changes proof bytes on this path is modelled - the
+    hash-to-field function of the BSB22 commitment challenge (SURVEY.md 8a "prover options")."""
+
+    def __init__(self, hash_kind):
+        self.hash_kind = hash_kind
+
+
+def WithProverHashToFieldFunction(kind):
+    """backend.WithProverHashToFieldFunction: 'default' (hash_to_field "bsb22-commitment") or 'solidity' (keccak256)."""
+    return ProverOption(kind)
+
+
+def WithProverTargetSolidityVerifier():
+    """solidity.WithProverTargetSolidityVerifier(backend.GROTH16) (circuits/statetransition/artifacts.go:18,
+    circuits/results/artifacts.go:17): keccak256 commitment hash, matching config/statetransition_vkey.sol:668-677."""
+    return ProverOption("solidity")
+
+
+def _hash_kind(opts):
+    kind = "default"
+    for o in opts:
+        if isinstance(o, ProverOption):
+            kind = o.hash_kind
+    return kind
+
+
+def _gpu_prove(curve_id, ccs: ConstraintSystem, pk: ProvingKey, w: Witness, device=-1, hash_kind="default"):
     if pk.curve_id != curve_id:
         raise ProverError("proving key type mismatch for curve %s: got a %s key" % (curve_id, pk.curve_id))
     L = Layout(curve_id)
@@ -123,7 +150,7 @@ def _gpu_prove(curve_id, ccs: ConstraintSystem, pk: ProvingKey, w: Witness, devi
         capi.check(capi.lib.b200_commit(handle, i, _slice(values_bytes, L.fr_bytes), out.ctypes.data, device))
         return out
 
-    sol = ccs.solve(w, commit_hint)            # raises on an unsatisfied constraint
+    sol = ccs.solve(w, commit_hint, hash_kind)            # raises on an unsatisfied constraint
     r, s = _randomness(curve_id)
     rb, sb = L.enc_fr([r]), L.enc_fr([s])
     pin = capi.ProveIn()
@@ -154,7 +181,7 @@ def _gpu_prove(curve_id, ccs: ConstraintSystem, pk: ProvingKey, w: Witness, devi
 def GPUProverWithWitness(curve, ccs, pk, w, *opts):
     """prover/prover_gpu.go:121-131 (the B200 path; errors are raised, never swallowed)."""
     try:
-        return _gpu_prove(curve, ccs, pk, w)
+        return _gpu_prove(curve, ccs, pk, w, hash_kind=_hash_kind(opts))
     except capi.B200Error as e:
         raise ProverError(str(e)) from e
 

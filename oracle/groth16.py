@@ -10,10 +10,11 @@ has a closed form in the exponent:
     Bs  = (beta  + sum_i w_i B_i(tau) + s delta) G2
     Krs = (sum_priv w_i K_i + h(tau) Z(tau)/delta - r s delta + s Ar + r Bs1) G1
 
-Parity status: UNPINNED by reference golden vectors (the reference never pins proof bytes, SURVEY.md
-fact 4).  Pinned mathematically instead: `verify_exponent` checks the Groth16 verifier equation
-e(A,B) = e(alpha,beta) e(L,gamma) e(C,delta) (config/statetransition_vkey.sol:596-626) in the
-exponent, plus the Pedersen knowledge check (`:678-699`).
+Parity status: gnark's own proof BYTES are unpinned (the reference never pins any, SURVEY.md fact 4, and gnark cannot
+be built here).  Everything else is pinned: `verify` is gnark's pairing verifier and `solidity_verify_proof` a
+line-by-line port of the contract the reference deploys (config/statetransition_vkey.sol:653-746) over the pairing
+oracle (oracle/pairing.py, itself pinned to reference-held material); `verify_exponent` re-checks the same equation in
+the exponent.  The commitment challenges use gnark's real hash-to-field functions (oracle/hashes.py).
 """
 import random
 from dataclasses import dataclass, field
@@ -37,7 +38,8 @@ class R1CS:
         return len(self.L)
 
 
-def synthetic_circuit(nb_constraints, nb_public, q, seed, n_commit=0, n_private_committed=0, mix="witness"):
+def synthetic_circuit(nb_constraints, nb_public, q, seed, n_commit=0, n_private_committed=0, mix="witness",
+                      n_public_committed=0):
     """'N multiplications + BSB22 commitments' circuit in the style of
     /root/reference/circuits/test/statetransition/statetransition_dummy.go:23-57, with a satisfying
     assignment.  Wire layout follows gnark: [one, public.., secret/internal..].
@@ -70,7 +72,9 @@ def synthetic_circuit(nb_constraints, nb_public, q, seed, n_commit=0, n_private_
     for ci in range(n_commit):
         priv = list(range(nxt, nxt + n_private_committed))
         nxt += n_private_committed
-        commitments.append({"private_committed": priv, "commitment_index": None})
+        # public committed wires only enter the challenge hash (gnark: PublicAndCommitmentCommitted)
+        commitments.append({"private_committed": priv, "commitment_index": None,
+                            "public_committed": list(range(1, 1 + min(n_public_committed, nb_public - 1)))})
     # commitment wires: value chosen by the (host-side) hash in the real prover; any value is a
     # valid assignment for the synthetic circuit because it only enters as a free factor.
     for cm in commitments:
@@ -203,6 +207,129 @@ def setup(cs: R1CS, cx: C.CurveCtx, tox: Toxic):
         ],
     }
     return pk, ex
+
+
+def verifying_key(cs: R1CS, cx: C.CurveCtx, tox: Toxic, ex=None):
+    """gnark groth16.VerifyingKey as points: G1 {Alpha, K[]}, G2 {Beta, Gamma, Delta}, and the Pedersen verifying keys
+    {G, GSigmaNeg = -sigma_i G} (gnark-crypto pedersen.VerifyingKey; the pairing check of
+    config/statetransition_vkey.sol:678-699 pairs the commitment with GSigmaNeg and the proof of knowledge with G)."""
+    ex = ex or setup_exponents(cs, cx, tox)
+    G1, G2, g1, g2 = cx.G1, cx.G2, cx.g1, cx.g2
+    return {
+        "G1": {"Alpha": G1.mul(g1, tox.alpha), "K": [G1.mul(g1, k) for k in ex["vk_K"]]},
+        "G2": {"Beta": G2.mul(g2, tox.beta), "Gamma": G2.mul(g2, tox.gamma), "Delta": G2.mul(g2, tox.delta)},
+        "CommitmentKeys": [{"G": g2, "GSigmaNeg": G2.neg(G2.mul(g2, sg))} for sg in tox.sigmas[:len(cs.commitments)]],
+        "nb_public": cs.nb_public,
+        "public_committed": [cm.get("public_committed", []) for cm in cs.commitments],
+    }
+
+
+# ----------------------------------------------------------------------------- verify (pairings)
+def verify(vk, proof, public_witness, cx: C.CurveCtx, hash_kind="default"):
+    """gnark groth16.Verify (reached from /root/reference/circuits/artifacts.go:595-613 right after every proof):
+    recomputes the commitment challenges from the proof's commitments and the public committed inputs, checks the
+    Pedersen proof of knowledge (folded with the "G16-BSB22" challenge when there are several commitments) and
+        e(Ar, Bs) = e(alpha, beta) * e(L, gamma) * e(Krs, delta),   L = sum_i pub_i K_i + sum_j chal_j K_(np+j) + sum_j C_j.
+    public_witness: the public wire values WITHOUT the constant-one wire (gnark's public witness vector)."""
+    from . import hashes as H
+    from . import pairing
+    pr = pairing.get(cx.name)
+    G1 = cx.G1
+    q = cx.r
+    pub = [1] + [int(v) % q for v in public_witness]
+    assert len(pub) == vk["nb_public"]
+    comms = proof["Commitments"]
+    if len(comms) != len(vk["CommitmentKeys"]):
+        return False
+    chals = [H.commitment_challenge(hash_kind, cm, [pub[w] for w in wires], q, cx.p)
+             for cm, wires in zip(comms, vk["public_committed"])]
+    if comms:
+        fold = H.fold_challenge(chals, q) if len(comms) > 1 else 1
+        pairs, f = [], 1
+        for cm, key in zip(comms, vk["CommitmentKeys"]):
+            pairs.append((G1.mul(cm, f), key["GSigmaNeg"]))
+            f = f * fold % q
+        pairs.append((proof["CommitmentPok"], vk["CommitmentKeys"][0]["G"]))
+        if not pr.product_is_one(pairs):
+            return False
+    L = G1.msm_naive(vk["G1"]["K"], pub + chals)
+    for cm in comms:
+        L = G1.add(L, cm)
+    return pr.product_is_one([(G1.neg(proof["Ar"]), proof["Bs"]), (vk["G1"]["Alpha"], vk["G2"]["Beta"]),
+                              (L, vk["G2"]["Gamma"]), (proof["Krs"], vk["G2"]["Delta"])])
+
+
+# ----------------------------------------------------------------------------- Solidity verifier (port)
+def solidity_constants(vk, cx: C.CurveCtx):
+    """The constant block gnark's Solidity exporter writes for a BN254 key with ONE commitment
+    (/root/reference/config/statetransition_vkey.sol:60-115): G2 points negated, Fp2 coordinates as (_0 real, _1 imaginary)."""
+    assert cx.name == "bn254" and len(vk["CommitmentKeys"]) == 1
+    G2 = cx.G2
+    c = {"ALPHA_X": vk["G1"]["Alpha"][0], "ALPHA_Y": vk["G1"]["Alpha"][1]}
+
+    def put2(name, pt):
+        (x0, x1), (y0, y1) = pt
+        c[name + "_X_0"], c[name + "_X_1"], c[name + "_Y_0"], c[name + "_Y_1"] = x0, x1, y0, y1
+
+    put2("BETA_NEG", G2.neg(vk["G2"]["Beta"]))
+    put2("GAMMA_NEG", G2.neg(vk["G2"]["Gamma"]))
+    put2("DELTA_NEG", G2.neg(vk["G2"]["Delta"]))
+    put2("PEDERSEN_G", vk["CommitmentKeys"][0]["G"])
+    put2("PEDERSEN_GSIGMANEG", vk["CommitmentKeys"][0]["GSigmaNeg"])
+    K = vk["G1"]["K"]
+    c["CONSTANT_X"], c["CONSTANT_Y"] = K[0]
+    for i, pt in enumerate(K[1:]):
+        c["PUB_%d_X" % i], c["PUB_%d_Y" % i] = pt
+    return c
+
+
+def solidity_verify_proof(c, proof8, commitments2, pok2, inputs, committed_input_indices, cx: C.CurveCtx):
+    """Line-by-line port of `verifyProof` (/root/reference/config/statetransition_vkey.sol:653-746) over the constant
+    block `c`: proof8 = A.x, A.y, B.x1, B.x0, B.y1, B.y0, C.x, C.y (EIP-197 order), commitments2 / pok2 = G1 points as
+    (x, y), inputs = the public inputs, committed_input_indices = which inputs are hashed into the commitment
+    challenge (the contract hard-codes input[2], `:663-666`).  Returns True where the contract would not revert."""
+    from . import hashes as H
+    from . import pairing
+    P_, R_ = cx.p, cx.r
+    pr = pairing.get("bn254")
+    G1 = cx.G1
+    if any(not (0 <= int(v) < R_) for v in inputs):
+        return False                                   # PublicInputNotInField
+    # HashToField (:660-677): keccak256(abi.encodePacked(commitments[0], commitments[1], publicAndCommitmentCommitted)) % R
+    packed = b"".join(int(v).to_bytes(32, "big") for v in list(commitments2) + [inputs[i] for i in committed_input_indices])
+    public_commitment = int.from_bytes(H.keccak256(packed), "big") % R_
+
+    def g1(x, y):
+        if x == 0 and y == 0:
+            return None
+        pt = (x % P_, y % P_)
+        if not G1.on_curve(pt):
+            raise ValueError("precompile failure: point not on curve")
+        return pt
+
+    def g2(x1, x0, y1, y0):                            # precompile order: imaginary part first
+        pt = ((x0, x1), (y0, y1))
+        if not cx.G2.on_curve(pt):
+            raise ValueError("precompile failure: G2 point not on curve")
+        return pt
+
+    cg2 = lambda n: g2(c[n + "_X_1"], c[n + "_X_0"], c[n + "_Y_1"], c[n + "_Y_0"])
+    try:
+        # Pedersen (:678-699): e(commitment, GSigmaNeg) * e(pok, G) == 1
+        if not pr.product_is_one([(g1(*commitments2), cg2("PEDERSEN_GSIGMANEG")), (g1(*pok2), cg2("PEDERSEN_G"))]):
+            return False                               # CommitmentInvalid
+        # publicInputMSM (:393-493): CONSTANT + commitment + sum input_i PUB_i + publicCommitments[0] PUB_last
+        acc = G1.add(g1(c["CONSTANT_X"], c["CONSTANT_Y"]), g1(*commitments2))
+        for i, v in enumerate(list(inputs) + [public_commitment]):
+            acc = G1.add(acc, G1.mul(g1(c["PUB_%d_X" % i], c["PUB_%d_Y" % i]), int(v)))
+        A = g1(proof8[0], proof8[1])
+        B = g2(proof8[2], proof8[3], proof8[4], proof8[5])
+        Cc = g1(proof8[6], proof8[7])
+        # (:700-746): e(A, B) * e(C, -delta) * e(alpha, -beta) * e(L_pub, -gamma) == 1
+        return pr.product_is_one([(A, B), (Cc, cg2("DELTA_NEG")), (g1(c["ALPHA_X"], c["ALPHA_Y"]), cg2("BETA_NEG")),
+                                  (acc, cg2("GAMMA_NEG"))])
+    except ValueError:
+        return False
 
 
 # ----------------------------------------------------------------------------- prove

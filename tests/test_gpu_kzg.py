@@ -136,3 +136,34 @@ def test_cell_proofs_vs_oracle(kz):
     want = OK.compute_cell_proofs(blob, mono, cells=[5, 126])
     assert got[5] == want[5] and got[126] == want[126]
     assert kz.Blob(bytes(4096 * 32)).ComputeCellProofs() == [bytes([0xC0]) + bytes(47)] * 128
+
+
+def test_gpu_openings_and_cell_proofs_verify_against_reference_tau_g2(kz):
+    """Reference-held check no oracle output enters: the GPU's opening proofs satisfy
+    e(C - [y]_1, G_2) = e(pi, [tau]_2 - [z]_2) with the [tau]_2 of /root/reference/crypto/blobs/kzg.go:26-45 and its cell
+    proofs e(C - [I_k(tau)]_1, G_2) = e(pi_k, [tau^64]_2 - [h_k^64]_2) with the SRS file's [tau^64]_2, for a random
+    statetransition-shaped blob (points outside and inside the evaluation domain, cells on both halves of the extension)."""
+    g2raw = open(os.path.join(GOLD, "kzg_g2_monomial.bin"), "rb").read()
+    g2 = lambda j: OK.g2_decompress(g2raw[96 * j:96 * (j + 1)])
+    mono_raw = open(os.path.join(GOLD, "kzg_g1_monomial.bin"), "rb").read()
+    kz.load_trusted_setup(open(os.path.join(GOLD, "kzg_g1_lagrange.bin"), "rb").read(), mono_raw)
+    mono64 = [OK.g1_decompress(mono_raw[48 * j:48 * (j + 1)]) for j in range(64)]
+    rnd = random.Random(31)
+    r = OP.BLS12_381.r
+    cells = [rnd.randrange(OP.BN254.r) for _ in range(2193)] + [0] * (4096 - 2193)
+    blob = b"".join(v.to_bytes(32, "big") for v in cells)
+    B = kz.Blob(blob)
+    commitment, cell_proofs = B.ComputeCommitmentAndCellProofs()
+    roots = OK.roots_of_unity_brp(4096)
+    for z in (rnd.randrange(r), roots[77]):
+        proof, y = B.ComputeProof(z)
+        assert OK.verify_kzg_proof(commitment, z, y, proof, g2(1)), hex(z)
+        assert not OK.verify_kzg_proof(commitment, z, (y + 1) % r, proof, g2(1))
+    # ComputeBlobProof = the opening at the Fiat-Shamir challenge
+    zc = OK.compute_challenge(blob, commitment)
+    bp = B.ComputeBlobProof(commitment)
+    assert OK.verify_kzg_proof(commitment, zc, OK.evaluate_in_evaluation_form(cells, zc, roots), bp, g2(1))
+    for k in (3, 100):
+        vals = OK.extended_cell_values(blob, k)
+        assert OK.verify_cell_proof(commitment, k, vals, cell_proofs[k], mono64, g2(64)), k
+    assert not OK.verify_cell_proof(commitment, 3, OK.extended_cell_values(blob, 4), cell_proofs[3], mono64, g2(64))

@@ -12,6 +12,15 @@ pytestmark = pytest.mark.gpu
 
 
 def _worker(rank, world, port, q):
+    try:
+        _worker_body(rank, world, port, q)
+    except BaseException as e:      # a dead worker must not leave the parent waiting for its queue entry
+        import traceback
+        q.put((rank, {"exception": False, "trace": traceback.format_exc()[-1500:]}))
+        raise
+
+
+def _worker_body(rank, world, port, q):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -86,9 +95,11 @@ def test_range_split_msm_nccl():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
+    res = [q.get(timeout=240) for _ in range(world)]
+    for rank, out in res:
+        assert "trace" not in out, out["trace"]
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
         assert p.exitcode == 0
     for rank, out in res:
         assert all(out.values()), (rank, out)

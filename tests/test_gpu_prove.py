@@ -21,34 +21,41 @@ def env():
 
 
 CASES = [
-    ("bls12_377", 60, 6, 1, 5, "witness"),     # voteverifier-shaped: 6 public wires, 1 commitment
-    ("bn254", 45, 9, 1, 4, "witness"),         # statetransition-shaped: 9 public + 1 commitment
-    ("bw6_761", 37, 2, 1, 3, "uniform"),       # aggregator-shaped
-    ("bls12_377", 130, 3, 0, 0, "uniform"),    # no commitment
-    ("bn254", 40, 3, 2, 3, "witness"),         # two commitments (folded proof of knowledge)
+    # curve, constraints, public wires, commitments, private committed, mix, commitment hash, public committed wires
+    ("bls12_377", 60, 6, 1, 5, "witness", "default", 0),     # voteverifier-shaped: 6 public wires, 1 commitment
+    ("bn254", 45, 9, 1, 4, "witness", "solidity", 1),        # statetransition-shaped: keccak target, input committed
+    ("bw6_761", 37, 2, 1, 3, "uniform", "default", 0),       # aggregator-shaped
+    ("bls12_377", 130, 3, 0, 0, "uniform", "default", 0),    # no commitment
+    ("bn254", 40, 3, 2, 3, "witness", "default", 1),         # two commitments (folded proof of knowledge)
 ]
 
 
-@pytest.mark.parametrize("cname,ncons,npub,ncommit,npc,mix", CASES)
-def test_prove_bit_exact_and_verifies(env, cname, ncons, npub, ncommit, npc, mix):
+@pytest.mark.parametrize("cname,ncons,npub,ncommit,npc,mix,hash_kind,npubc", CASES)
+def test_prove_bit_exact_and_verifies(env, cname, ncons, npub, ncommit, npc, mix, hash_kind, npubc):
+    """With (r, s) pinned the GPU proof equals the oracle's restatement of gnark's Prove bit for bit; pinned or not it
+    passes gnark's verifier (pairings, real commitment hashes) and - BN254 with one commitment - the port of the
+    Solidity verifier the reference deploys."""
     from oracle_bridge import ccs_from_oracle, pk_from_oracle
     capi, layout, prover, T = env
     cx = OC.ctx(cname)
     q = cx.r
     L = layout.Layout(cname)
     rnd = random.Random(hash((cname, ncons)) & 0xFFFF)
-    cs, W0 = OG.synthetic_circuit(ncons, npub, q, seed=ncons, n_commit=ncommit, n_private_committed=npc, mix=mix)
+    cs, W0 = OG.synthetic_circuit(ncons, npub, q, seed=ncons, n_commit=ncommit, n_private_committed=npc, mix=mix,
+                                  n_public_committed=npubc)
     tox = OG.Toxic(*(rnd.randrange(1, q) for _ in range(5)), sigmas=[rnd.randrange(1, q) for _ in range(ncommit)])
     opk, ex = OG.setup(cs, cx, tox)
+    vk = OG.verifying_key(cs, cx, tox, ex)
     ccs = ccs_from_oracle(cs, L.id)
     pk = pk_from_oracle(opk, L.id)
     w = T.Witness(L.id, W0[1:cs.nb_public], W0[cs.nb_public:cs.nb_public + ccs.nb_secret])
+    opts = [prover.WithProverTargetSolidityVerifier()] if hash_kind == "solidity" else []
     r, s = rnd.randrange(q), rnd.randrange(q)
     prover.SetRandomness(lambda cid: (r, s))
     try:
-        proof = prover.ProveWithWitness(L.id, ccs, pk, w)
+        proof = prover.ProveWithWitness(L.id, ccs, pk, w, *opts)
         # the solver (host) fixed the commitment-wire values; replay the same assignment in the oracle
-        sol = ccs.solve(w, lambda i, v: proof.Commitments[i])
+        sol = ccs.solve(w, lambda i, v: proof.Commitments[i], hash_kind)
         W = sol.values
         want = OG.prove(cs, opk, W, r, s, cx, fold_challenge=sol.fold_challenge)
         got = proof.points()
@@ -61,10 +68,25 @@ def test_prove_bit_exact_and_verifies(env, cname, ncons, npub, ncommit, npc, mix
         A, B, Cx = OG.proof_exponents(cs, ex, tox, W, r, s, q)
         assert got["Ar"] == cx.G1.mul(cx.g1, A) and got["Bs"] == cx.G2.mul(cx.g2, B)
         assert OG.verify_exponent(cs, ex, tox, W, A, B, Cx, q)
-        # un-pinned randomness: a different valid proof that still satisfies the verifier equation
+        public = W[1:cs.nb_public]
+        assert OG.verify(vk, got, public, cx, hash_kind)
+        # un-pinned randomness: a different proof that passes the same verifiers
         prover.SetRandomness(None)
-        p2 = prover.ProveWithWitness(L.id, ccs, pk, w).points()
+        p2 = prover.ProveWithWitness(L.id, ccs, pk, w, *opts).points()
         assert p2["Ar"] != got["Ar"]
+        assert OG.verify(vk, p2, public, cx, hash_kind)
+        wrong = list(public)
+        wrong[-1] = (wrong[-1] + 1) % q
+        assert not OG.verify(vk, p2, wrong, cx, hash_kind)
+        if cname == "bn254" and ncommit == 1 and hash_kind == "solidity":
+            consts = OG.solidity_constants(vk, cx)
+            Ar, Bs, Krs = p2["Ar"], p2["Bs"], p2["Krs"]
+            proof8 = [Ar[0], Ar[1], Bs[0][1], Bs[0][0], Bs[1][1], Bs[1][0], Krs[0], Krs[1]]
+            committed_inputs = [wire - 1 for wire in cs.commitments[0]["public_committed"]]
+            assert OG.solidity_verify_proof(consts, proof8, p2["Commitments"][0], p2["CommitmentPok"], public,
+                                            committed_inputs, cx)
+            assert not OG.solidity_verify_proof(consts, proof8, p2["Commitments"][0], p2["CommitmentPok"], wrong,
+                                                committed_inputs, cx)
     finally:
         prover.SetRandomness(None)
         prover.release_proving_key(pk)
