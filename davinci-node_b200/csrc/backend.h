@@ -127,7 +127,8 @@ struct MsmStats {
 };
 
 enum FieldSel { FIELD_FP = 0, FIELD_FR = 1, FIELD_FP2 = 2 };
-enum FieldOp { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_SQR = 3, OP_FROM_MONT = 4, OP_TO_MONT = 5, OP_INV = 6, OP_NEG = 7 };
+enum FieldOp { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_SQR = 3, OP_FROM_MONT = 4, OP_TO_MONT = 5, OP_INV = 6, OP_NEG = 7,
+               OP_SQRT = 8 };   // sqrt: a root, or zero when the input is not a square
 enum EcOp { EC_MADD = 0, EC_ADD = 1, EC_DBL = 2, EC_TO_AFFINE = 3, EC_MUL_SCALAR = 4 };
 
 // Device-resident evaluation domain of size 2^logn (twiddle / coset-power tables live in HBM).
@@ -212,6 +213,11 @@ struct CurveBackend {
   // --- EIP-4844 helpers (BLS12-381 only; other curves throw)
   virtual void g1_decompress(const void* d_bytes, void* d_affine, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;
   virtual void g1_compress(const void* d_affine, void* d_bytes, uint32_t n, cudaStream_t s) = 0;
+  // gnark-crypto compressed points of any curve / group (serde.cuh): the on-disk format of proving keys.
+  // d_err: bit 0 bad encoding, bit 1 not on the curve
+  virtual size_t compressed_bytes(int group) const = 0;
+  virtual void points_decompress(int group, const void* d_bytes, void* d_affine, uint64_t n, uint32_t* d_err, cudaStream_t s) = 0;
+  virtual void points_compress(int group, const void* d_affine, void* d_bytes, uint64_t n, cudaStream_t s) = 0;
   virtual void blob_to_scalars(const void* d_blob, void* d_scalars, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;
   // KZG opening (EIP-4844 compute_kzg_proof_impl): roots = w^brp(i) table; kzg_open turns the blob's scalars p and
   // the point z (32 big-endian bytes on the device) into the quotient evaluations q and y = p(z) (32 bytes).

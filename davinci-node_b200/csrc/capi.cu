@@ -520,6 +520,26 @@ int b200_blob_proof(uint64_t h, const uint8_t* blob, const uint8_t point_be[32],
   });
 }
 
+// ---------------------------------------------------------------------------------- key artefacts
+uint64_t b200_compressed_bytes(int c, int g) { return backend_by_id(c) && (g == 1 || g == 2) ? backend_by_id(c)->compressed_bytes(g) : 0; }
+
+int b200_points_decompress_dev(int curve_id, int group, const void* d_bytes, uint64_t n, void* d_affine_out,
+                               uint32_t* d_err_flags, void* stream) {
+  return guarded([&] {
+    check_group(group);
+    if (n && (!d_bytes || !d_affine_out || !d_err_flags)) throw std::runtime_error("null argument");
+    curve(curve_id).points_decompress(group, d_bytes, d_affine_out, n, d_err_flags, (cudaStream_t)stream);
+  });
+}
+
+int b200_points_compress_dev(int curve_id, int group, const void* d_affine, uint64_t n, void* d_bytes_out, void* stream) {
+  return guarded([&] {
+    check_group(group);
+    if (n && (!d_affine || !d_bytes_out)) throw std::runtime_error("null argument");
+    curve(curve_id).points_compress(group, d_affine, d_bytes_out, n, (cudaStream_t)stream);
+  });
+}
+
 // ---------------------------------------------------------------------------------- setup / instrumentation
 int b200_fixed_base_dev(int curve_id, int group, const void* d_base_affine, const void* d_scalars, uint64_t n,
                         void* d_out_affine, void* stream) {

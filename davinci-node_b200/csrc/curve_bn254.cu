@@ -10,6 +10,18 @@ struct Cfg_bn254 {
   using Fr = FpT<bn254_fr>;
   using G1F = Fp;
   using G2F = Fp2T<bn254_fp, 1>;
+  static constexpr int FLAG_BITS = 2;   // gnark-crypto point-compression flag bits (serde.cuh)
+  // E: y^2 = x^3 + 3 ; D-twist E': y^2 = x^3 + 3/(9+u)
+  static __device__ void curve_b(typename G1F::El& b1, typename G2F::El& b2) {
+    typename G1F::El one;
+    G1F::set_one(one);
+    G1F::mul_small(b1, one, 3);
+    typename G2F::El xi;
+    G1F::mul_small(xi.c0, one, 9);
+    xi.c1 = one;
+    G2F::inv(xi, xi);
+    G2F::mul_small(b2, xi, 3);
+  }
 };
 
 CurveBackend* backend_bn254() {

@@ -9,6 +9,10 @@
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "kzg.cuh"
+#include "serde.cuh"
+#include <memory>
+#include <map>
+#include <mutex>
 
 namespace b200 {
 
@@ -26,6 +30,9 @@ __global__ void k_dbg_field(int op, const typename F::El* a, const typename F::E
     case OP_SQR: F::sqr(r, x); break;
     case OP_INV: F::inv(r, x); break;
     case OP_NEG: F::neg(r, x); break;
+    case OP_SQRT:
+      if (!F::sqrt(r, x)) F::set_zero(r);
+      break;
     default: r = x; break;
   }
   out[i] = r;
@@ -138,6 +145,16 @@ __global__ void __launch_bounds__(256) k_calib_mul(typename F::El* io, uint64_t 
   }
   F::add(x, x, y);
   io[i] = x;
+}
+
+template <class Cfg>
+__global__ void k_curve_consts(typename Cfg::G1F::El* b1, typename Cfg::G2F::El* b2) {
+  if (threadIdx.x || blockIdx.x) return;
+  typename Cfg::G1F::El x;
+  typename Cfg::G2F::El y;
+  Cfg::curve_b(x, y);
+  *b1 = x;
+  *b2 = y;
 }
 
 // ------------------------------------------------------------------------------------ proof assembly
@@ -744,6 +761,52 @@ struct CurveImpl : CurveBackend {
     const NttScale none{SCALE_NONE, 0, nullptr, nullptr, nullptr};
     NttScale ci{SCALE_POW_BITREV, d.lo_bits, d.gi_lo.p, d.gi_hi_scaled.p, nullptr};
     run_passes<false>(d.logn, (FrEl*)d_a, (const FrEl*)d.tw_inv.p, none, ci, (const FrEl*)d_b, (const FrEl*)d_c, consts + 3, s);
+  }
+
+  // ---------------------------------------------------------------- point (de)compression, all curves
+  // curve coefficients b (G1) and b' (G2), computed once per device
+  std::mutex consts_mu;
+  std::map<int, std::unique_ptr<DevBuf>> curve_consts;
+  const uint8_t* curve_b_dev(cudaStream_t s) {
+    int dev = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(consts_mu);
+    auto& slot = curve_consts[dev];
+    if (!slot) {
+      slot.reset(new DevBuf());
+      uint8_t* p = (uint8_t*)slot->get(sizeof(typename G1F::El) + sizeof(typename G2F::El));
+      k_curve_consts<Cfg><<<1, 1, 0, s>>>((typename G1F::El*)p, (typename G2F::El*)(p + sizeof(typename G1F::El)));
+      B200_CUDA(cudaGetLastError());
+      B200_CUDA(cudaStreamSynchronize(s));
+    }
+    return (const uint8_t*)slot->p;
+  }
+  size_t compressed_bytes(int group) const override {
+    return group == 1 ? (size_t)CoordSerde<G1F>::BYTES : (size_t)CoordSerde<G2F>::BYTES;
+  }
+  void points_decompress(int group, const void* d_bytes, void* d_affine, uint64_t n, uint32_t* d_err,
+                         cudaStream_t s) override {
+    if (!n) return;
+    const uint8_t* cb = curve_b_dev(s);
+    const unsigned blocks = (unsigned)((n + 63) / 64);
+    if (group == 1)
+      k_points_decompress<G1F><<<blocks, 64, 0, s>>>((const uint8_t*)d_bytes, (Affine<G1F>*)d_affine, n, Cfg::FLAG_BITS,
+                                                     (const typename G1F::El*)cb, d_err);
+    else
+      k_points_decompress<G2F><<<blocks, 64, 0, s>>>((const uint8_t*)d_bytes, (Affine<G2F>*)d_affine, n, Cfg::FLAG_BITS,
+                                                     (const typename G2F::El*)(cb + sizeof(typename G1F::El)), d_err);
+    prof_count_launches(1);
+    B200_CUDA(cudaGetLastError());
+  }
+  void points_compress(int group, const void* d_affine, void* d_bytes, uint64_t n, cudaStream_t s) override {
+    if (!n) return;
+    const unsigned blocks = (unsigned)((n + 63) / 64);
+    if (group == 1)
+      k_points_compress<G1F><<<blocks, 64, 0, s>>>((const Affine<G1F>*)d_affine, (uint8_t*)d_bytes, n, Cfg::FLAG_BITS);
+    else
+      k_points_compress<G2F><<<blocks, 64, 0, s>>>((const Affine<G2F>*)d_affine, (uint8_t*)d_bytes, n, Cfg::FLAG_BITS);
+    prof_count_launches(1);
+    B200_CUDA(cudaGetLastError());
   }
 
   void g1_decompress(const void* d_bytes, void* d_affine, uint32_t n, uint32_t* d_err, cudaStream_t s) override {

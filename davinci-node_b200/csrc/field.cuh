@@ -131,6 +131,42 @@ struct FpT {
     }
     r = acc;
   }
+  // Tonelli-Shanks square root (any odd p; one exponentiation when p = 3 mod 4).  Returns false - and leaves r
+  // unspecified - when a is not a square.  Used by point decompression.
+  static __device__ __noinline__ bool sqrt(El& r, const El& a) {
+    if (is_zero(a)) {
+      set_zero(r);
+      return true;
+    }
+    uint32_t e[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) e[i] = P::sqrt_e(i);
+    El w, x, b, z, one;
+    set_one(one);
+    pow<N>(w, a, e);          // a^((T-1)/2)
+    mul(x, a, w);             // a^((T+1)/2)
+    mul(b, x, w);             // a^T
+#pragma unroll
+    for (int i = 0; i < N; i++) z.v[i] = P::sqrt_z(i);
+    int rr = P::TWO_ADICITY;
+    while (!eq(b, one)) {
+      int m = 0;
+      El t = b;
+      while (!eq(t, one) && m < rr) {
+        sqr(t, t);
+        m++;
+      }
+      if (m >= rr) return false;
+      El g = z;
+      for (int k = 0; k < rr - m - 1; k++) sqr(g, g);
+      mul(x, x, g);
+      sqr(z, g);
+      mul(b, b, z);
+      rr = m;
+    }
+    r = x;
+    return true;
+  }
   // a^-1 = a^(p-2); 0 -> 0
   static __device__ __noinline__ void inv(El& r, const El& a) {
     uint32_t e[N];
@@ -226,6 +262,64 @@ struct Fp2T {
   static __device__ __forceinline__ void mul_small(El& r, const El& a, int k) {
     Base::mul_small(r.c0, a.c0, k);
     Base::mul_small(r.c1, a.c1, k);
+  }
+  // square root in Fp2 through the norm (u^2 = -NR_NEG is a non-residue of Fp); false when a is not a square.
+  // (the two cases run one after the other under plain ifs: see the control-flow rule in ec.cuh)
+  static __device__ __noinline__ bool sqrt(El& r, const El& a) {
+    const bool real_only = Base::is_zero(a.c1);
+    bool ok = false;
+    if (!real_only) {
+      BEl half, two, t, n, s, x0, x1;
+      Base::sqr(n, a.c0);
+      Base::sqr(t, a.c1);
+      mul_nr_neg(t, t);
+      Base::add(n, n, t);                    // norm = a0^2 + NR_NEG a1^2
+      bool have = Base::sqrt(s, n);
+      if (have) {
+        Base::set_one(two);
+        Base::dbl(two, two);
+        Base::inv(half, two);
+        Base::add(t, a.c0, s);
+        Base::mul(t, t, half);               // (a0 + s) / 2
+        have = Base::sqrt(x0, t);
+        if (!have) {
+          Base::sub(t, a.c0, s);
+          Base::mul(t, t, half);             // (a0 - s) / 2
+          have = Base::sqrt(x0, t);
+        }
+      }
+      if (have) {
+        Base::dbl(t, x0);
+        Base::inv(t, t);
+        Base::mul(x1, a.c1, t);              // a1 / (2 x0)
+        r.c0 = x0;
+        r.c1 = x1;
+        El chk;
+        sqr(chk, r);
+        ok = eq(chk, a);
+      }
+    }
+    if (real_only) {
+      BEl t, x;
+      bool direct = Base::sqrt(x, a.c0);
+      if (direct) {
+        r.c0 = x;
+        Base::set_zero(r.c1);
+        ok = true;
+      }
+      if (!direct) {
+        // sqrt(a0) = u sqrt(a0 / u^2) = u sqrt(-a0 / NR_NEG)
+        Base::set_one(t);
+        mul_nr_neg(t, t);
+        Base::inv(t, t);
+        Base::mul(t, t, a.c0);
+        Base::neg(t, t);
+        ok = Base::sqrt(x, t);
+        Base::set_zero(r.c0);
+        r.c1 = x;
+      }
+    }
+    return ok;
   }
   static __device__ __noinline__ void inv(El& r, const El& a) {
     // 1/(a0 + a1 u) = (a0 - a1 u) / (a0^2 + NR_NEG a1^2)

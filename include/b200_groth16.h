@@ -215,6 +215,19 @@ B200_API int b200_blob_cell_proofs(uint64_t srs, const uint8_t* blob, uint8_t* p
 B200_API int b200_blob_proof(uint64_t srs, const uint8_t* blob, const uint8_t point_be[32], uint8_t proof_out[48],
                              uint8_t claim_out[32], int device);
 
+/* ---- proving-key artefacts ----------------------------------------------------------------------------
+ * gnark-crypto compressed points -> affine points in memory layout, on the device, for any curve and group: the bulk of
+ * loading a proving key written by pk.WriteTo (cmd/circuit-compile/main.go:507-512) and read at
+ * circuits/artifacts.go:391-406 (pk.UnsafeReadFrom: ~10^7 square roots on the CPU in the reference).  Encoding: big-endian
+ * X (G2 over Fp2: X.A1 || X.A0), flags in the top bits of byte 0 (BN254: 2 bits, the others 3).
+ * d_err_flags (one uint32, zeroed by the caller) gets bit 0 = bad encoding, bit 1 = not on the curve.  compress is the
+ * inverse (pk.WriteTo). */
+B200_API uint64_t b200_compressed_bytes(int curve, int group);
+B200_API int b200_points_decompress_dev(int curve, int group, const void* d_bytes, uint64_t n, void* d_affine_out,
+                                        uint32_t* d_err_flags, void* cuda_stream);
+B200_API int b200_points_compress_dev(int curve, int group, const void* d_affine, uint64_t n, void* d_bytes_out,
+                                      void* cuda_stream);
+
 /* ---- setup building block / instrumentation -----------------------------------------------------
  * out[i] = [k_i] base as affine points: the fixed-base batch scalar multiplication groth16.Setup is
  * made of (prover/setup.go:15-28 -> groth16.Setup).  Device pointers. */
@@ -238,7 +251,7 @@ B200_API int b200_profile_collect(double ms_out[5], uint64_t count_out[5]);
 B200_API int b200_profile_timeline(double* out, uint64_t cap_records, uint64_t* n_out);
 
 /* ---- debug / parity entry points (device pointers; element-wise over n items) ---------------
- * field: 0 = Fp, 1 = Fr, 2 = Fp2 ; op: 0 add, 1 sub, 2 mul, 3 sqr, 4 from_mont, 5 to_mont, 6 inv, 7 neg */
+ * field: 0 = Fp, 1 = Fr, 2 = Fp2 ; op: 0 add, 1 sub, 2 mul, 3 sqr, 4 from_mont, 5 to_mont, 6 inv, 7 neg, 8 sqrt (zero when not a square) */
 B200_API int b200_dbg_field_op_dev(int curve, int field, int op, const void* d_a, const void* d_b, void* d_out, uint64_t n,
                           void* cuda_stream);
 /* op: 0 madd (xyzz += affine), 1 add (xyzz += xyzz), 2 dbl, 3 to_affine, 4 mul by Fr scalar */

@@ -85,6 +85,15 @@ def test_prove_bit_exact_and_verifies(env, cname, ncons, npub, ncommit, npc, mix
             committed_inputs = [wire - 1 for wire in cs.commitments[0]["public_committed"]]
             assert OG.solidity_verify_proof(consts, proof8, p2["Commitments"][0], p2["CommitmentPok"], public,
                                             committed_inputs, cx)
+            # the on-chain calldata (solidity/solidity.go:85-116 mirror) carries exactly these words
+            from davinci_node_b200 import solidity
+            prover.SetRandomness(lambda cid: (r, s))
+            sp = solidity.Groth16CommitmentProof().FromGnarkProof(prover.ProveWithWitness(L.id, ccs, pk, w, *opts))
+            prover.SetRandomness(None)
+            data = sp.ABIEncode()
+            assert len(data) == 384 and solidity.Groth16CommitmentProof.ABIDecode(data).words() == sp.words()
+            wds = sp.words()
+            assert OG.solidity_verify_proof(consts, wds[:8], wds[8:10], wds[10:12], public, committed_inputs, cx)
             assert not OG.solidity_verify_proof(consts, proof8, p2["Commitments"][0], p2["CommitmentPok"], wrong,
                                                 committed_inputs, cx)
     finally:

@@ -122,3 +122,30 @@ def test_bench_reference_arm_contract_and_no_cpu_fallback():
         r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1", "--logn", "10"],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def test_solidity_abi_encoding():
+    """solidity/solidity.go:29-116 mirror: word order (B's imaginary parts first), 384-byte static ABI layout."""
+    import json
+    from davinci_node_b200 import gnark_types as T, solidity
+    from davinci_node_b200.layout import Layout
+    from oracle import curve as OC
+    cx = OC.ctx("bn254")
+    L = Layout(1)
+    g1 = lambda k: cx.G1.mul(cx.g1, k)
+    proof = T.Proof(1)
+    proof.Ar, proof.Krs, proof.CommitmentPok = L.enc_affine([g1(3)], 1), L.enc_affine([g1(5)], 1), L.enc_affine([g1(7)], 1)
+    bs = cx.G2.mul(cx.g2, 11)
+    proof.Bs = L.enc_affine([bs], 2)
+    proof.Commitments = [L.enc_affine([g1(9)], 1)]
+    sp = solidity.Groth16CommitmentProof().FromGnarkProof(proof)
+    data = sp.ABIEncode()
+    assert len(data) == 12 * 32
+    w = [int.from_bytes(data[32 * i:32 * i + 32], "big") for i in range(12)]
+    assert w[0:2] == list(g1(3)) and w[6:8] == list(g1(5)) and w[8:10] == list(g1(9)) and w[10:12] == list(g1(7))
+    assert w[2:6] == [bs[0][1], bs[0][0], bs[1][1], bs[1][0]]
+    assert solidity.Groth16CommitmentProof.ABIDecode(data).words() == w
+    assert json.loads(sp.String())["proof"]["Bs"][0] == [bs[0][1], bs[0][0]]
+    bad = T.Proof(2)
+    with pytest.raises(solidity.SolidityProofError):
+        solidity.Groth16CommitmentProof().FromGnarkProof(bad)

@@ -473,6 +473,17 @@ def emit_field(name, p, n):
     hdr.append(arr("r2", (R * R) % p))        # to-Montgomery multiplier
     hdr.append(arr("r3", (R * R * R) % p))
     hdr.append("  static constexpr uint32_t M0 = 0x%08xu;" % ((-pow(p, -1, 1 << 32)) & MASK))
+    # Tonelli-Shanks constants (point decompression): p - 1 = 2^S * T, sqrt_e = (T - 1) / 2, sqrt_z = nqr^T (Montgomery)
+    S_, T_ = 0, p - 1
+    while T_ % 2 == 0:
+        T_ //= 2
+        S_ += 1
+    nqr = 2
+    while pow(nqr, (p - 1) // 2, p) != p - 1:
+        nqr += 1
+    hdr.append("  static constexpr int TWO_ADICITY = %d;" % S_)
+    hdr.append(arr("sqrt_e", (T_ - 1) // 2))
+    hdr.append(arr("sqrt_z", pow(nqr, T_, p) * R % p))
     hdr.append(emit_fn(progs["add"], "add", n, 2))
     hdr.append(emit_fn(progs["sub"], "sub", n, 2))
     hdr.append(emit_fn(progs["mul"], "mul", n, 2))
