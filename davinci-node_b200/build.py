@@ -10,15 +10,17 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libb200groth16.so")
+# B200_BUILD_TAG=<name> builds an experiment variant (extra flags from B200_EXTRA_NVCC_FLAGS) next to the product library
+_TAG = os.environ.get("B200_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(HERE, "libb200groth16%s.so" % ("_" + _TAG if _TAG else ""))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-I", CSRC, "-I", os.path.join(ROOT, "include"),
-]
+] + os.environ.get("B200_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _newest(paths):

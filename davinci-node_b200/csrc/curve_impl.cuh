@@ -48,43 +48,38 @@ __global__ void k_dbg_field_mont(int op, const typename F::El* a, typename F::El
   out[i] = r;
 }
 
-template <class F, class Fr>
-__global__ void k_dbg_ec(int op, const void* a, const void* b, void* out, uint64_t n) {
+// one kernel per operation (a single kernel switching over the operations shares one stack frame between unrelated
+// cases; the scalar multiplication of BN254 - where Fr and Fp elements are the same C++ type - came out wrong that way)
+template <class F, class Fr, int OP>
+__global__ void k_dbg_ec(const void* a, const void* b, void* out, uint64_t n) {
   using E = EC<F>;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   XYZZ<F> p = reinterpret_cast<const XYZZ<F>*>(a)[i];
-  switch (op) {
-    case EC_MADD: {
-      Affine<F> q = reinterpret_cast<const Affine<F>*>(b)[i];
-      E::madd(p, q);
-      reinterpret_cast<XYZZ<F>*>(out)[i] = p;
-      break;
-    }
-    case EC_ADD: {
-      XYZZ<F> q = reinterpret_cast<const XYZZ<F>*>(b)[i];
-      E::add(p, q);
-      reinterpret_cast<XYZZ<F>*>(out)[i] = p;
-      break;
-    }
-    case EC_DBL:
-      E::dbl(p);
-      reinterpret_cast<XYZZ<F>*>(out)[i] = p;
-      break;
-    case EC_TO_AFFINE: {
-      Affine<F> q;
-      E::to_affine(q, p);
-      reinterpret_cast<Affine<F>*>(out)[i] = q;
-      break;
-    }
-    case EC_MUL_SCALAR: {
-      typename Fr::El s = reinterpret_cast<const typename Fr::El*>(b)[i], sc;
-      Fr::from_mont(sc, s);
-      XYZZ<F> r;
-      E::template mul_scalar<Fr::N>(r, p, sc.v);
-      reinterpret_cast<XYZZ<F>*>(out)[i] = r;
-      break;
-    }
+  if constexpr (OP == EC_MADD) {
+    Affine<F> q = reinterpret_cast<const Affine<F>*>(b)[i];
+    E::madd(p, q);
+    reinterpret_cast<XYZZ<F>*>(out)[i] = p;
+  } else if constexpr (OP == EC_ADD) {
+    XYZZ<F> q = reinterpret_cast<const XYZZ<F>*>(b)[i];
+    E::add(p, q);
+    reinterpret_cast<XYZZ<F>*>(out)[i] = p;
+  } else if constexpr (OP == EC_DBL) {
+    E::dbl(p);
+    reinterpret_cast<XYZZ<F>*>(out)[i] = p;
+  } else if constexpr (OP == EC_TO_AFFINE) {
+    Affine<F> q;
+    E::to_affine(q, p);
+    reinterpret_cast<Affine<F>*>(out)[i] = q;
+  } else {
+    typename Fr::El s = reinterpret_cast<const typename Fr::El*>(b)[i], sc;
+    Fr::from_mont(sc, s);
+    uint32_t k[Fr::N];
+#pragma unroll
+    for (int j = 0; j < Fr::N; j++) k[j] = sc.v[j];
+    XYZZ<F> r;
+    E::template mul_scalar<Fr::N>(r, p, k);
+    reinterpret_cast<XYZZ<F>*>(out)[i] = r;
   }
 }
 
@@ -294,11 +289,8 @@ __global__ void __launch_bounds__(64) k_build_tables(const Affine<F>* __restrict
     load16_rw(pre, sc + 2);
     Affine<F> xy, o;
     load16_rw(xy, tables + (uint64_t)j * npts + i);
-    if (F::is_zero(zz)) {
-      F::set_zero(o.x);
-      F::set_zero(o.y);
-      F::set_one(d);
-    } else {
+    {
+      // (no branch around the products: for G2 they are out-of-line calls, see the control-flow rule in ec.cuh)
       F::mul(dinv, rinv, pre);             // 1 / (ZZ_j ZZZ_j)
       El izz, izzz;
       F::mul(izz, dinv, zzz);
@@ -306,6 +298,11 @@ __global__ void __launch_bounds__(64) k_build_tables(const Affine<F>* __restrict
       F::mul(o.x, xy.x, izz);
       F::mul(o.y, xy.y, izzz);
       F::mul(d, zz, zzz);
+      if (F::is_zero(zz)) {
+        F::set_zero(o.x);
+        F::set_zero(o.y);
+        F::set_one(d);
+      }
     }
     F::mul(rinv, rinv, d);
     store16(tables + (uint64_t)j * npts + i, o);
@@ -970,11 +967,22 @@ struct CurveImpl : CurveBackend {
     } else throw std::runtime_error("bad field selector");
   }
 
+  template <class F>
+  static void dbg_ec_launch(int op, const void* a, const void* b, void* out, uint64_t n, cudaStream_t s) {
+    const unsigned blocks = (unsigned)((n + 31) / 32);
+    switch (op) {
+      case EC_MADD: k_dbg_ec<F, Fr, EC_MADD><<<blocks, 32, 0, s>>>(a, b, out, n); break;
+      case EC_ADD: k_dbg_ec<F, Fr, EC_ADD><<<blocks, 32, 0, s>>>(a, b, out, n); break;
+      case EC_DBL: k_dbg_ec<F, Fr, EC_DBL><<<blocks, 32, 0, s>>>(a, b, out, n); break;
+      case EC_TO_AFFINE: k_dbg_ec<F, Fr, EC_TO_AFFINE><<<blocks, 32, 0, s>>>(a, b, out, n); break;
+      case EC_MUL_SCALAR: k_dbg_ec<F, Fr, EC_MUL_SCALAR><<<blocks, 32, 0, s>>>(a, b, out, n); break;
+      default: throw std::runtime_error("bad EC op");
+    }
+  }
   void dbg_ec_op(int group, int op, const void* a, const void* b, void* out, uint64_t n, cudaStream_t s) override {
     if (!n) return;
-    unsigned blocks = (unsigned)((n + 31) / 32);
-    if (group == 1) k_dbg_ec<G1F, Fr><<<blocks, 32, 0, s>>>(op, a, b, out, n);
-    else k_dbg_ec<G2F, Fr><<<blocks, 32, 0, s>>>(op, a, b, out, n);
+    if (group == 1) dbg_ec_launch<G1F>(op, a, b, out, n, s);
+    else dbg_ec_launch<G2F>(op, a, b, out, n, s);
     B200_CUDA(cudaGetLastError());
   }
 

@@ -73,7 +73,9 @@ struct EC {
 
   // p = 2 * p                   (dbl-2008-s-1)
   static __device__ __noinline__ void dbl(Pt& p) {
-    if (is_inf(p)) return;
+    // no early exit for the point at infinity: ZZ' = V ZZ = 0 keeps it at infinity (Fp2 products are calls, see the
+    // control-flow rule below), X and Y are zeroed at the end for hygiene
+    const bool inf = is_inf(p);
     El u, v, w, s, m, t;
     F::dbl(u, p.y);
     F::sqr(v, u);
@@ -91,98 +93,158 @@ struct EC {
     F::sub(p.y, t, u);
     F::mul(p.zz, v, p.zz);
     F::mul(p.zzz, w, p.zzz);
+    if (inf) set_inf(p);
   }
 
-  // Control-flow rule for everything below: an out-of-line call (dbl, dbl_affine, the Fp2 products) never sits in a
-  // branch whose sibling threads keep executing other code of the same function.  ptxas keeps warp-uniform values
-  // (stack addresses, the Montgomery constant) in per-WARP uniform registers; a callee entered by a divergent subset
-  // overwrites them under the feet of the threads still running the caller's main path (found with compute-sanitizer:
-  // add() -> dbl() loaded M0 into the UR holding add()'s frame pointer).  So the special cases are classified first,
-  // the generic path runs under a plain `if`, and the rare doubling call comes last, where every other thread of the
-  // warp waits at the reconvergence point.
+  // Control-flow rule for everything below: a branch that encloses an OUT-OF-LINE call (dbl, dbl_affine, the Fp2
+  // products) must be warp-uniform.  ptxas keeps warp-uniform values - stack addresses of by-reference arguments, the
+  // Montgomery constant - in per-WARP uniform registers, and a callee entered by a divergent subset of a warp
+  // overwrites them under the feet of the sibling threads that are still on another path of the caller (found with
+  // compute-sanitizer: add() -> dbl() loaded M0 into the uniform register holding add()'s frame pointer; rewriting the
+  // source as "plain ifs" does not help, the optimiser re-threads the paths).  So: the case of every thread is
+  // classified first, each piece of arithmetic runs when ANY thread of the converged group needs it (warp vote), and
+  // every thread keeps its own result with selects.
   enum : int { kModeSkip = 0, kModeCopy = 1, kModeGeneric = 2, kModeDouble = 3, kModeCancel = 4 };
 
-  // acc += (affine p)           (madd-2008-s), all special cases handled
-  static __device__ __forceinline__ void madd(Pt& acc, const Aff& p) {
-    El u2, s2;
-    int mode;
-    if (is_inf(p)) {
-      mode = kModeSkip;
-    } else if (is_inf(acc)) {
-      mode = kModeCopy;
-    } else {
-      F::mul(u2, p.x, acc.zz);
-      F::mul(s2, p.y, acc.zzz);
-      F::sub(u2, u2, acc.x);     // P
-      F::sub(s2, s2, acc.y);     // R
-      mode = !F::is_zero(u2) ? kModeGeneric : (F::is_zero(s2) ? kModeDouble : kModeCancel);
-    }
-    if (mode == kModeGeneric) {
-      El pp, ppp, q, t;
-      F::sqr(pp, u2);
-      F::mul(ppp, u2, pp);
-      F::mul(q, acc.x, pp);
-      F::sqr(t, s2);
-      F::sub(t, t, ppp);
-      F::sub(t, t, q);
-      F::sub(acc.x, t, q);       // X3 = R^2 - PPP - 2Q
-      F::sub(q, q, acc.x);
-      F::mul(q, s2, q);          // R (Q - X3)
-      F::mul(t, acc.y, ppp);
-      F::sub(acc.y, q, t);
-      F::mul(acc.zz, acc.zz, pp);
-      F::mul(acc.zzz, acc.zzz, ppp);
-    } else if (mode == kModeCopy) {
-      acc.x = p.x;
-      acc.y = p.y;
-      F::set_one(acc.zz);
-      F::set_one(acc.zzz);
-    } else if (mode == kModeCancel) {
-      set_inf(acc);
-    }
-    if (mode == kModeDouble) dbl_affine(acc, p);
+  static __device__ __forceinline__ void csel(El& dst, const El& src, bool take) {
+    uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(&src);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(El) / 4); i++) d[i] = take ? q[i] : d[i];
+  }
+  static __device__ __forceinline__ void csel(Pt& dst, const Pt& src, bool take) {
+    csel(dst.x, src.x, take);
+    csel(dst.y, src.y, take);
+    csel(dst.zz, src.zz, take);
+    csel(dst.zzz, src.zzz, take);
   }
 
-  // acc += b                    (add-2008-s), all special cases handled
+  // acc += (affine p)           (madd-2008-s), all special cases handled.  The hot path of the bucket accumulation:
+  // plain early exits and inline products; the (rare, out-of-line) doubling is deferred to the end and entered by vote.
+  static __device__ __forceinline__ void madd(Pt& acc, const Aff& p) {
+    bool need_dbl = false;
+    if (!is_inf(p)) {
+      if (is_inf(acc)) {
+        acc.x = p.x;
+        acc.y = p.y;
+        F::set_one(acc.zz);
+        F::set_one(acc.zzz);
+      } else {
+        El u2, s2, pp, ppp, q, t;
+        F::mul(u2, p.x, acc.zz);
+        F::mul(s2, p.y, acc.zzz);
+        F::sub(u2, u2, acc.x);     // P
+        F::sub(s2, s2, acc.y);     // R
+        if (F::is_zero(u2)) {
+          need_dbl = F::is_zero(s2);
+          if (!need_dbl) set_inf(acc);
+        } else {
+          F::sqr(pp, u2);
+          F::mul(ppp, u2, pp);
+          F::mul(q, acc.x, pp);
+          F::sqr(t, s2);
+          F::sub(t, t, ppp);
+          F::sub(t, t, q);
+          F::sub(acc.x, t, q);       // X3 = R^2 - PPP - 2Q
+          F::sub(q, q, acc.x);
+          F::mul(q, s2, q);          // R (Q - X3)
+          F::mul(t, acc.y, ppp);
+          F::sub(acc.y, q, t);
+          F::mul(acc.zz, acc.zz, pp);
+          F::mul(acc.zzz, acc.zzz, ppp);
+        }
+      }
+    }
+    if (__any_sync(__activemask(), need_dbl)) {     // every thread of the converged group makes the call
+      Pt d;
+      dbl_affine(d, p);
+      csel(acc, d, need_dbl);
+    }
+  }
+
+  // acc += b                    (add-2008-s), all special cases handled; every branch around arithmetic is a vote
   static __device__ __noinline__ void add(Pt& acc, const Pt& b) {
+    const unsigned grp = __activemask();
+    const bool b_inf = is_inf(b), a_inf = is_inf(acc);
+    const bool live = !b_inf && !a_inf;
+    int mode = b_inf ? kModeSkip : kModeCopy;
     El u1, u2, s1, s2;
-    int mode;
-    if (is_inf(b)) {
-      mode = kModeSkip;
-    } else if (is_inf(acc)) {
-      mode = kModeCopy;
-    } else {
+    if (__any_sync(grp, live)) {
       F::mul(u1, acc.x, b.zz);
       F::mul(u2, b.x, acc.zz);
       F::mul(s1, acc.y, b.zzz);
       F::mul(s2, b.y, acc.zzz);
       F::sub(u2, u2, u1);        // P
       F::sub(s2, s2, s1);        // R
-      mode = !F::is_zero(u2) ? kModeGeneric : (F::is_zero(s2) ? kModeDouble : kModeCancel);
+      if (live) mode = !F::is_zero(u2) ? kModeGeneric : (F::is_zero(s2) ? kModeDouble : kModeCancel);
     }
-    if (mode == kModeGeneric) {
+    if (__any_sync(grp, mode == kModeGeneric)) {
       El pp, ppp, q, t;
+      Pt r3;
       F::sqr(pp, u2);
       F::mul(ppp, u2, pp);
       F::mul(q, u1, pp);
       F::sqr(t, s2);
       F::sub(t, t, ppp);
       F::sub(t, t, q);
-      F::sub(acc.x, t, q);
-      F::sub(q, q, acc.x);
+      F::sub(r3.x, t, q);
+      F::sub(q, q, r3.x);
       F::mul(q, s2, q);
       F::mul(t, s1, ppp);
-      F::sub(acc.y, q, t);
-      F::mul(acc.zz, acc.zz, b.zz);
-      F::mul(acc.zz, acc.zz, pp);
-      F::mul(acc.zzz, acc.zzz, b.zzz);
-      F::mul(acc.zzz, acc.zzz, ppp);
-    } else if (mode == kModeCopy) {
-      acc = b;
-    } else if (mode == kModeCancel) {
-      set_inf(acc);
+      F::sub(r3.y, q, t);
+      F::mul(r3.zz, acc.zz, b.zz);
+      F::mul(r3.zz, r3.zz, pp);
+      F::mul(r3.zzz, acc.zzz, b.zzz);
+      F::mul(r3.zzz, r3.zzz, ppp);
+      csel(acc, r3, mode == kModeGeneric);
     }
-    if (mode == kModeDouble) dbl(acc);
+    csel(acc, b, mode == kModeCopy);
+    if (mode == kModeCancel) set_inf(acc);
+    if (__any_sync(grp, mode == kModeDouble)) {
+      Pt d = acc;
+      dbl(d);
+      csel(acc, d, mode == kModeDouble);
+    }
+  }
+
+  // acc += b with plain early exits: ONLY for callers whose warp-mates cannot be on a sibling path - the one-thread
+  // proof-assembly kernels and the scalar-multiplication helpers below (control-flow rule above)
+  static __device__ __noinline__ void add_st(Pt& acc, const Pt& b) {
+    if (is_inf(b)) return;
+    if (is_inf(acc)) {
+      acc = b;
+      return;
+    }
+    El u1, u2, s1, s2, pp, ppp, q, t;
+    F::mul(u1, acc.x, b.zz);
+    F::mul(u2, b.x, acc.zz);
+    F::mul(s1, acc.y, b.zzz);
+    F::mul(s2, b.y, acc.zzz);
+    F::sub(u2, u2, u1);        // P
+    F::sub(s2, s2, s1);        // R
+    if (F::is_zero(u2)) {
+      if (F::is_zero(s2)) {
+        dbl(acc);
+      } else {
+        set_inf(acc);
+      }
+      return;
+    }
+    F::sqr(pp, u2);
+    F::mul(ppp, u2, pp);
+    F::mul(q, u1, pp);
+    F::sqr(t, s2);
+    F::sub(t, t, ppp);
+    F::sub(t, t, q);
+    F::sub(acc.x, t, q);
+    F::sub(q, q, acc.x);
+    F::mul(q, s2, q);
+    F::mul(t, s1, ppp);
+    F::sub(acc.y, q, t);
+    F::mul(acc.zz, acc.zz, b.zz);
+    F::mul(acc.zz, acc.zz, pp);
+    F::mul(acc.zzz, acc.zzz, b.zzz);
+    F::mul(acc.zzz, acc.zzz, ppp);
   }
 
   // r = [k] p for a small unsigned k (double-and-add, MSB first)
@@ -191,7 +253,7 @@ struct EC {
     set_inf(acc);
     for (int i = 31; i >= 0; i--) {
       dbl(acc);
-      if ((k >> i) & 1) add(acc, p);
+      if ((k >> i) & 1) add_st(acc, p);
     }
     r = acc;
   }
@@ -205,7 +267,7 @@ struct EC {
     for (int i = NS * 32 - 1; i >= 0; i--) {
       if (started) dbl(acc);
       if ((s[i >> 5] >> (i & 31)) & 1) {
-        add(acc, p);
+        add_st(acc, p);
         started = true;
       }
     }
@@ -224,7 +286,7 @@ struct EC {
       tab[k] = tab[k >> 1];
       if (k & 1) {
         tab[k] = tab[k - 1];
-        add(tab[k], p);
+        add_st(tab[k], p);
       } else {
         dbl(tab[k]);
       }
@@ -241,7 +303,7 @@ struct EC {
       }
       uint32_t d = (s[i >> 3] >> ((i & 7) * 4)) & 15u;
       if (d) {
-        add(acc, tab[d]);
+        add_st(acc, tab[d]);
         started = true;
       }
     }

@@ -264,61 +264,68 @@ struct Fp2T {
     Base::mul_small(r.c1, a.c1, k);
   }
   // square root in Fp2 through the norm (u^2 = -NR_NEG is a non-residue of Fp); false when a is not a square.
-  // (the two cases run one after the other under plain ifs: see the control-flow rule in ec.cuh)
+  // Every branch around the out-of-line base-field calls is a warp vote and each thread selects its own result
+  // (control-flow rule in ec.cuh).
+  static __device__ __forceinline__ void bsel(BEl& dst, const BEl& src, bool take) {
+#pragma unroll
+    for (int i = 0; i < P::N; i++) dst.v[i] = take ? src.v[i] : dst.v[i];
+  }
   static __device__ __noinline__ bool sqrt(El& r, const El& a) {
+    const unsigned grp = __activemask();
     const bool real_only = Base::is_zero(a.c1);
     bool ok = false;
-    if (!real_only) {
-      BEl half, two, t, n, s, x0, x1;
+    El out;
+    set_zero(out);
+    if (__any_sync(grp, !real_only)) {
+      BEl half, two, t, n, s, x0, x0b, x1;
       Base::sqr(n, a.c0);
       Base::sqr(t, a.c1);
       mul_nr_neg(t, t);
       Base::add(n, n, t);                    // norm = a0^2 + NR_NEG a1^2
       bool have = Base::sqrt(s, n);
-      if (have) {
-        Base::set_one(two);
-        Base::dbl(two, two);
-        Base::inv(half, two);
-        Base::add(t, a.c0, s);
-        Base::mul(t, t, half);               // (a0 + s) / 2
-        have = Base::sqrt(x0, t);
-        if (!have) {
-          Base::sub(t, a.c0, s);
-          Base::mul(t, t, half);             // (a0 - s) / 2
-          have = Base::sqrt(x0, t);
-        }
+      Base::set_one(two);
+      Base::dbl(two, two);
+      Base::inv(half, two);
+      Base::add(t, a.c0, s);
+      Base::mul(t, t, half);                 // (a0 + s) / 2
+      const bool first = Base::sqrt(x0, t);
+      if (__any_sync(grp, have && !first)) {
+        Base::sub(t, a.c0, s);
+        Base::mul(t, t, half);               // (a0 - s) / 2
+        const bool second = Base::sqrt(x0b, t);
+        bsel(x0, x0b, !first);
+        have = have && (first || second);
       }
-      if (have) {
-        Base::dbl(t, x0);
-        Base::inv(t, t);
-        Base::mul(x1, a.c1, t);              // a1 / (2 x0)
-        r.c0 = x0;
-        r.c1 = x1;
-        El chk;
-        sqr(chk, r);
-        ok = eq(chk, a);
-      }
+      Base::dbl(t, x0);
+      Base::inv(t, t);
+      Base::mul(x1, a.c1, t);                // a1 / (2 x0)
+      El cand, chk;
+      cand.c0 = x0;
+      cand.c1 = x1;
+      sqr(chk, cand);
+      const bool good = !real_only && have && eq(chk, a);
+      bsel(out.c0, cand.c0, good);
+      bsel(out.c1, cand.c1, good);
+      ok = ok || good;
     }
-    if (real_only) {
-      BEl t, x;
-      bool direct = Base::sqrt(x, a.c0);
-      if (direct) {
-        r.c0 = x;
-        Base::set_zero(r.c1);
-        ok = true;
-      }
-      if (!direct) {
-        // sqrt(a0) = u sqrt(a0 / u^2) = u sqrt(-a0 / NR_NEG)
-        Base::set_one(t);
-        mul_nr_neg(t, t);
-        Base::inv(t, t);
-        Base::mul(t, t, a.c0);
-        Base::neg(t, t);
-        ok = Base::sqrt(x, t);
-        Base::set_zero(r.c0);
-        r.c1 = x;
-      }
+    if (__any_sync(grp, real_only)) {
+      BEl t, x, xi, zero;
+      Base::set_zero(zero);
+      const bool direct = Base::sqrt(x, a.c0);
+      // sqrt(a0) = u sqrt(a0 / u^2) = u sqrt(-a0 / NR_NEG)
+      Base::set_one(t);
+      mul_nr_neg(t, t);
+      Base::inv(t, t);
+      Base::mul(t, t, a.c0);
+      Base::neg(t, t);
+      const bool imag = Base::sqrt(xi, t);
+      bsel(out.c0, x, real_only && direct);
+      bsel(out.c1, zero, real_only && direct);
+      bsel(out.c0, zero, real_only && !direct && imag);
+      bsel(out.c1, xi, real_only && !direct && imag);
+      ok = ok || (real_only && (direct || imag));
     }
+    r = out;
     return ok;
   }
   static __device__ __noinline__ void inv(El& r, const El& a) {

@@ -89,24 +89,24 @@ k_points_decompress(const uint8_t* __restrict__ in, Affine<F>* __restrict__ out,
   Affine<F> r;
   F::set_zero(r.x);
   F::set_zero(r.y);
-  bool ok = true;
-  if (flags == pf.smallest || flags == pf.largest) {
-    El x, y2, y;
+  const bool compressed = flags == pf.smallest || flags == pf.largest;
+  // the square root is an out-of-line call: entered by every thread of the converged group when any needs it
+  if (__any_sync(__activemask(), compressed)) {
+    El x, y2, y, ny;
     S::read(x, buf);
     F::sqr(y2, x);
     F::mul(y2, y2, x);
     F::add(y2, y2, *curve_b);
-    if (F::sqrt(y, y2)) {
-      if (S::largest(y) != (flags == pf.largest)) F::neg(y, y);
+    const bool found = F::sqrt(y, y2);
+    F::neg(ny, y);
+    const bool flip = S::largest(y) != (flags == pf.largest);
+    if (compressed && found) {
       r.x = x;
-      r.y = y;
-    } else {
-      atomicOr(err, 2u);
+      r.y = flip ? ny : y;
     }
-  } else if (flags != pf.infinity) {
-    ok = false;
+    if (compressed && !found) atomicOr(err, 2u);
   }
-  if (!ok) atomicOr(err, 1u);
+  if (!compressed && flags != pf.infinity) atomicOr(err, 1u);
   store16(out + i, r);
 }
 

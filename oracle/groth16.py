@@ -277,9 +277,9 @@ def solidity_constants(vk, cx: C.CurveCtx):
     put2("PEDERSEN_G", vk["CommitmentKeys"][0]["G"])
     put2("PEDERSEN_GSIGMANEG", vk["CommitmentKeys"][0]["GSigmaNeg"])
     K = vk["G1"]["K"]
-    c["CONSTANT_X"], c["CONSTANT_Y"] = K[0]
+    c["CONSTANT_X"], c["CONSTANT_Y"] = K[0] or (0, 0)
     for i, pt in enumerate(K[1:]):
-        c["PUB_%d_X" % i], c["PUB_%d_Y" % i] = pt
+        c["PUB_%d_X" % i], c["PUB_%d_Y" % i] = pt or (0, 0)        # (0, 0) is the precompiles' point at infinity
     return c
 
 
@@ -321,7 +321,9 @@ def solidity_verify_proof(c, proof8, commitments2, pok2, inputs, committed_input
         # publicInputMSM (:393-493): CONSTANT + commitment + sum input_i PUB_i + publicCommitments[0] PUB_last
         acc = G1.add(g1(c["CONSTANT_X"], c["CONSTANT_Y"]), g1(*commitments2))
         for i, v in enumerate(list(inputs) + [public_commitment]):
-            acc = G1.add(acc, G1.mul(g1(c["PUB_%d_X" % i], c["PUB_%d_Y" % i]), int(v)))
+            pub_i = g1(c["PUB_%d_X" % i], c["PUB_%d_Y" % i])
+            if pub_i is not None:
+                acc = G1.add(acc, G1.mul(pub_i, int(v)))
         A = g1(proof8[0], proof8[1])
         B = g2(proof8[2], proof8[3], proof8[4], proof8[5])
         Cc = g1(proof8[6], proof8[7])
