@@ -128,7 +128,8 @@ struct MsmStats {
 
 enum FieldSel { FIELD_FP = 0, FIELD_FR = 1, FIELD_FP2 = 2 };
 enum FieldOp { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_SQR = 3, OP_FROM_MONT = 4, OP_TO_MONT = 5, OP_INV = 6, OP_NEG = 7,
-               OP_SQRT = 8 };   // sqrt: a root, or zero when the input is not a square
+               OP_SQRT = 8,     // sqrt: a root, or zero when the input is not a square
+               OP_INV_BIN = 9 };  // binary-GCD inversion (the one-thread path of the proof assembly)
 enum EcOp { EC_MADD = 0, EC_ADD = 1, EC_DBL = 2, EC_TO_AFFINE = 3, EC_MUL_SCALAR = 4 };
 
 // Device-resident evaluation domain of size 2^logn (twiddle / coset-power tables live in HBM).

@@ -33,6 +33,7 @@ __global__ void k_dbg_field(int op, const typename F::El* a, const typename F::E
     case OP_SQRT:
       if (!F::sqrt(r, x)) F::set_zero(r);
       break;
+    case OP_INV_BIN: F::inv_bin(r, x); break;
     default: r = x; break;
   }
   out[i] = r;
@@ -95,7 +96,7 @@ __global__ void k_sum_partials(const XYZZ<F>* in, uint32_t count, Affine<F>* out
     EC<F>::add(acc, p);
   }
   Affine<F> o;
-  EC<F>::to_affine(o, acc);
+  EC<F>::template to_affine<true>(o, acc);
   *out = o;
 }
 
@@ -201,19 +202,19 @@ __global__ void k_assemble_out(const XYZZ<F1>* ar, const XYZZ<F2>* bs2, const XY
     EC<F1>::add(acc, tmp[0]);
     EC<F1>::add(acc, tmp[1]);
     Affine<F1> o;
-    EC<F1>::to_affine(o, acc);
+    EC<F1>::template to_affine<true>(o, acc);
     *out_krs = o;
   } else if (blockIdx.x == 1) {
     Affine<F1> o;
-    EC<F1>::to_affine(o, *ar);
+    EC<F1>::template to_affine<true>(o, *ar);
     *out_ar = o;
   } else if (blockIdx.x == 2) {
     Affine<F2> o;
-    EC<F2>::to_affine(o, *bs2);
+    EC<F2>::template to_affine<true>(o, *bs2);
     *out_bs = o;
   } else if (pok && out_pok) {
     Affine<F1> o;
-    EC<F1>::to_affine(o, *pok);
+    EC<F1>::template to_affine<true>(o, *pok);
     *out_pok = o;
   }
 }
@@ -671,27 +672,51 @@ struct CurveImpl : CurveBackend {
     return v;
   }
 
+  // passes [first, last) of the transform's plan; `pre` applies to pass 0 and `post` to the final pass of the WHOLE plan
+  // (so a caller running a sub-range only gets them when the range touches that end)
   template <bool DIT>
   static void run_passes(int logn, FrEl* data, const FrEl* tw, NttScale pre, NttScale post, const FrEl* in_b,
-                         const FrEl* in_c, const FrEl* den, cudaStream_t s) {
+                         const FrEl* in_c, const FrEl* den, cudaStream_t s, int first_pass = 0, int last_pass = -1) {
     // per-device attribute; cheap enough to set on every call (device pools live in one process)
     B200_CUDA(cudaFuncSetAttribute(k_ntt_pass<Fr, DIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(sizeof(FrEl) << kElogMax)));
     auto passes = plan_passes(logn, DIT);
+    if (last_pass < 0) last_pass = (int)passes.size();
     const NttScale none{SCALE_NONE, 0, nullptr, nullptr, nullptr};
-    for (size_t i = 0; i < passes.size(); i++) {
+    for (int i = first_pass; i < last_pass; i++) {
       const NttPass& ps = passes[i];
       int elog = ps.logr + ps.lo_tile_log;
       unsigned blocks = 1u << (logn - elog);
       size_t smem = sizeof(FrEl) << elog;
-      bool first = i == 0, last = i + 1 == passes.size();
+      bool first = i == 0, last = i + 1 == (int)passes.size();
       const int tok = prof_begin(PROF_NTT_PASS, s);
       k_ntt_pass<Fr, DIT><<<blocks, kNttThreads, smem, s>>>(data, tw, ps, first ? pre : none, last ? post : none,
                                                            first ? in_b : nullptr, first ? in_c : nullptr, den);
       prof_end(tok, s);
     }
-    prof_count_launches(passes.size());
+    prof_count_launches(last_pass - first_pass);
     B200_CUDA(cudaGetLastError());
+  }
+
+  // "interpolate, then evaluate on the coset" for one vector: inverse DIF without its last (contiguous) pass, the fused
+  // middle (k_ntt_fused_mid), coset DIT without its first pass and - when `skip_last_dit` - without its last one
+  // (which the fused quotient kernel performs).  npasses = passes of one plain transform.
+  static void coset_evals_fused(NttDomain& d, FrEl* v, bool skip_last_dit, cudaStream_t s) {
+    const NttScale none{SCALE_NONE, 0, nullptr, nullptr, nullptr};
+    const FrEl* twf = (const FrEl*)d.tw_fwd.p;
+    const FrEl* twi = (const FrEl*)d.tw_inv.p;
+    const NttScale cs{SCALE_POW_BITREV, d.lo_bits, d.g_lo.p, d.g_hi_scaled.p, nullptr};
+    auto dit = plan_passes(d.logn, true);
+    const int np = (int)dit.size();
+    run_passes<false>(d.logn, v, twi, none, none, nullptr, nullptr, nullptr, s, 0, np - 1);
+    const NttPass& mid = dit[0];                       // contiguous pass: s_log = 0, lo_tile_log = 0
+    const size_t smem = sizeof(FrEl) << mid.logr;
+    B200_CUDA(cudaFuncSetAttribute(k_ntt_fused_mid<Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tok = prof_begin(PROF_NTT_PASS, s);
+    k_ntt_fused_mid<Fr><<<1u << (d.logn - mid.logr), kNttThreads, smem, s>>>(v, twi, twf, mid, cs);
+    prof_end(tok, s);
+    prof_count_launches(1);
+    run_passes<true>(d.logn, v, twf, none, none, nullptr, nullptr, nullptr, s, 1, skip_last_dit ? np - 1 : np);
   }
 
   void domain_init(NttDomain& d, int logn, const void* d_omega, const void* d_g, cudaStream_t s) override {
@@ -736,17 +761,41 @@ struct CurveImpl : CurveBackend {
     const FrEl* twf = (const FrEl*)d.tw_fwd.p;
     const FrEl* twi = (const FrEl*)d.tw_inv.p;
     FrEl* v[3] = {(FrEl*)d_a, (FrEl*)d_b, (FrEl*)d_c};
-    // 1. interpolate (unscaled inverse DIF: natural -> bit-reversed coefficients times n)
-    for (int k = 0; k < 3; k++) run_passes<false>(d.logn, v[k], twi, none, none, nullptr, nullptr, nullptr, s);
-    // 2. evaluate on the coset g*<omega>: scale by g^i / n on load, DIT: bit-reversed -> natural
-    NttScale cs{SCALE_POW_BITREV, d.lo_bits, d.g_lo.p, d.g_hi_scaled.p, nullptr};
-    for (int k = 0; k < 3; k++) run_passes<true>(d.logn, v[k], twf, cs, none, nullptr, nullptr, nullptr, s);
-    // 3. (a*b - c) / (g^n - 1) fused into the load of the inverse coset transform; g^-i / n on store
+    // (a*b - c) / (g^n - 1) on the coset, then back: g^-i / n on store of the last inverse pass
     NttScale ci{SCALE_POW_BITREV, d.lo_bits, d.gi_lo.p, d.gi_hi_scaled.p, nullptr};
-    run_passes<false>(d.logn, v[0], twi, none, ci, v[1], v[2], consts + 3, s);
+    auto dit = plan_passes(d.logn, true);
+    const int np = (int)dit.size();
+    static const bool fuse = [] {
+      const char* e = std::getenv("B200_NTT_FUSE");   // 0 restores the 21-pass schedule (A/B measurements)
+      return !(e && std::atoi(e) == 0);
+    }();
+    if (np < 2 || !fuse) {
+      // one pass per transform (n <= 2^11) or fusion disabled: the plain 7-transform schedule
+      for (int k = 0; k < 3; k++) run_passes<false>(d.logn, v[k], twi, none, none, nullptr, nullptr, nullptr, s);
+      NttScale cs{SCALE_POW_BITREV, d.lo_bits, d.g_lo.p, d.g_hi_scaled.p, nullptr};
+      for (int k = 0; k < 3; k++) run_passes<true>(d.logn, v[k], twf, cs, none, nullptr, nullptr, nullptr, s);
+      run_passes<false>(d.logn, v[0], twi, none, ci, v[1], v[2], consts + 3, s);
+      return;
+    }
+    // 15 passes instead of 21 at three passes per transform: per vector  (np - 1) + 1 fused + (np - 2),  then ONE fused
+    // pass (last DIT level group of a, b, c + pointwise + first DIF level group), then the remaining np - 1 DIF passes
+    for (int k = 0; k < 3; k++) coset_evals_fused(d, v[k], true, s);
+    const NttPass& ps = dit[np - 1];                    // == first pass of the DIF plan
+    const int elog = ps.logr + ps.lo_tile_log;
+    const size_t smem = 3 * (sizeof(FrEl) << elog);
+    B200_CUDA(cudaFuncSetAttribute(k_ntt_fused_quot<Fr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tok = prof_begin(PROF_NTT_PASS, s);
+    k_ntt_fused_quot<Fr><<<1u << (d.logn - elog), kNttQuotThreads, smem, s>>>(v[0], v[1], v[2], twf, twi, ps, consts + 3);
+    prof_end(tok, s);
+    prof_count_launches(1);
+    run_passes<false>(d.logn, v[0], twi, none, ci, nullptr, nullptr, nullptr, s, 1, np);
   }
 
   void coset_evals(NttDomain& d, void* d_v, cudaStream_t s) override {
+    if (plan_passes(d.logn, true).size() >= 2) {
+      coset_evals_fused(d, (FrEl*)d_v, false, s);
+      return;
+    }
     const NttScale none{SCALE_NONE, 0, nullptr, nullptr, nullptr};
     run_passes<false>(d.logn, (FrEl*)d_v, (const FrEl*)d.tw_inv.p, none, none, nullptr, nullptr, nullptr, s);
     NttScale cs{SCALE_POW_BITREV, d.lo_bits, d.g_lo.p, d.g_hi_scaled.p, nullptr};

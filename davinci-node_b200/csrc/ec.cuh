@@ -312,6 +312,8 @@ struct EC {
 
   // affine normalisation: x = X/ZZ, y = Y/ZZZ ; infinity -> (0, 0).  Inlined (the inversion inside
   // is the only out-of-line call) and written through a local with a single exit.
+  // SINGLE_THREAD: the caller is a one-thread kernel (proof assembly) - use the low-latency binary-GCD inversion
+  template <bool SINGLE_THREAD = false>
   static __device__ __forceinline__ void to_affine(Aff& r, const Pt& p) {
     Aff o;
     F::set_zero(o.x);
@@ -320,7 +322,8 @@ struct EC {
       // 1/ZZ and 1/ZZZ from a single inversion of ZZ*ZZZ
       El t, ti, izz, izzz;
       F::mul(t, p.zz, p.zzz);
-      F::inv(ti, t);
+      if (SINGLE_THREAD) F::inv_bin(ti, t);
+      else F::inv(ti, t);
       F::mul(izz, ti, p.zzz);
       F::mul(izzz, ti, p.zz);
       F::mul(o.x, p.x, izz);

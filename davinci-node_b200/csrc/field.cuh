@@ -167,6 +167,81 @@ struct FpT {
     r = x;
     return true;
   }
+  // a^-1 by the binary extended Euclidean algorithm on the canonical value (~2 log2 p iterations of N-limb shifts and
+  // subtractions): ~10x less latency than the Fermat exponentiation for ONE thread (the proof's final affine
+  // normalisation); data-dependent loops, so not for warps of independent elements.  0 -> 0.
+  static __device__ __noinline__ void inv_bin(El& r, const El& a) {
+    uint32_t u[N], v[N], x1[N], x2[N];
+    El ac;
+    from_mont(ac, a);
+    bool zero = true;
+    for (int i = 0; i < N; i++) {
+      u[i] = ac.v[i];
+      v[i] = P::modulus(i);
+      x1[i] = i == 0;
+      x2[i] = 0;
+      zero = zero && u[i] == 0;
+    }
+    if (zero) {
+      set_zero(r);
+      return;
+    }
+    auto is_one = [](const uint32_t* w) {
+      uint32_t o = w[0] ^ 1u;
+      for (int i = 1; i < N; i++) o |= w[i];
+      return o == 0;
+    };
+    auto shr1 = [](uint32_t* w) {
+      for (int i = 0; i < N - 1; i++) w[i] = (w[i] >> 1) | (w[i + 1] << 31);
+      w[N - 1] >>= 1;
+    };
+    auto add_p = [](uint32_t* w) {           // w += p  (w < p, 2p < 2^(32N) for every field here)
+      uint64_t c = 0;
+      for (int i = 0; i < N; i++) {
+        c += (uint64_t)w[i] + P::modulus(i);
+        w[i] = (uint32_t)c;
+        c >>= 32;
+      }
+    };
+    auto geq = [](const uint32_t* a_, const uint32_t* b_) {
+      for (int i = N - 1; i >= 0; i--) {
+        if (a_[i] != b_[i]) return a_[i] > b_[i];
+      }
+      return true;
+    };
+    auto sub = [](uint32_t* a_, const uint32_t* b_) {     // a -= b, returns the borrow
+      uint64_t bw = 0;
+      for (int i = 0; i < N; i++) {
+        uint64_t t = (uint64_t)a_[i] - b_[i] - bw;
+        a_[i] = (uint32_t)t;
+        bw = (t >> 32) & 1u;
+      }
+      return (uint32_t)bw;
+    };
+    while (!is_one(u) && !is_one(v)) {
+      while (!(u[0] & 1u)) {
+        shr1(u);
+        if (x1[0] & 1u) add_p(x1);
+        shr1(x1);
+      }
+      while (!(v[0] & 1u)) {
+        shr1(v);
+        if (x2[0] & 1u) add_p(x2);
+        shr1(x2);
+      }
+      if (geq(u, v)) {
+        sub(u, v);
+        if (sub(x1, x2)) add_p(x1);          // x1 = x1 - x2 mod p
+      } else {
+        sub(v, u);
+        if (sub(x2, x1)) add_p(x2);
+      }
+    }
+    El out;
+    const uint32_t* res = is_one(u) ? x1 : x2;
+    for (int i = 0; i < N; i++) out.v[i] = res[i];
+    to_mont(r, out);
+  }
   // a^-1 = a^(p-2); 0 -> 0
   static __device__ __noinline__ void inv(El& r, const El& a) {
     uint32_t e[N];
@@ -327,6 +402,17 @@ struct Fp2T {
     }
     r = out;
     return ok;
+  }
+  static __device__ __noinline__ void inv_bin(El& r, const El& a) {
+    BEl n, t;
+    Base::sqr(n, a.c0);
+    Base::sqr(t, a.c1);
+    mul_nr_neg(t, t);
+    Base::add(n, n, t);
+    Base::inv_bin(n, n);
+    Base::mul(r.c0, a.c0, n);
+    Base::mul(t, a.c1, n);
+    Base::neg(r.c1, t);
   }
   static __device__ __noinline__ void inv(El& r, const El& a) {
     // 1/(a0 + a1 u) = (a0 - a1 u) / (a0^2 + NR_NEG a1^2)

@@ -1,6 +1,7 @@
 // Radix-2^k number-theoretic transforms over Fr for sm_100a.
 //
-// A transform of size n = 2^logn runs as 1-3 passes; each pass stages a tile of up to 2^11
+// A transform of size n = 2^logn runs as 1-3 passes (the quotient's 7 transforms as 15 instead of 21: see the fused
+// kernels below); each pass stages a tile of up to 2^11
 // elements in shared memory and performs up to 11 butterfly levels there (twiddles ω^k, k < n/2,
 // are a table resident in HBM / L2).  Strided passes load `lo_tile` consecutive elements per row so
 // global accesses stay in >= 256-byte runs.  DIF (Gentleman-Sande, natural -> bit-reversed) and DIT
@@ -69,6 +70,56 @@ __device__ __forceinline__ void ntt_apply_scale(typename Fr::El& x, const NttSca
   Fr::mul(x, x, l);
 }
 
+// ps.logr butterfly levels over a tile of 2^(logr + lo_tile_log) elements held chunk-major in shared memory; ends with
+// a barrier.  lo0: position of the tile's first column inside its row group (twiddle exponents depend on it).
+template <class Fr, bool DIT>
+__device__ __forceinline__ void ntt_tile_levels(uint4* sm, const NttPass& ps, const typename Fr::El* __restrict__ tw,
+                                                uint32_t lo0) {
+  using El = typename Fr::El;
+  const uint32_t E = 1u << (ps.logr + ps.lo_tile_log);
+  const uint32_t lo_mask = (1u << ps.lo_tile_log) - 1u;
+  const uint32_t half = E >> 1;
+  for (int j = 0; j < ps.logr; j++) {
+    const int log_dm = DIT ? j : (ps.logr - 1 - j);
+    const int shift = ps.logn - 1 - ps.s_log - log_dm;   // twiddle exponent scale: d * 2^shift = n/2
+    const uint32_t dm_mask = (1u << log_dm) - 1u;
+    for (uint32_t q = threadIdx.x; q < half; q += blockDim.x) {
+      uint32_t lo_l = q & lo_mask;
+      uint32_t u = q >> ps.lo_tile_log;
+      uint32_t mid_low = u & dm_mask;
+      uint32_t mid = ((u >> log_dm) << (log_dm + 1)) | mid_low;
+      uint32_t i0 = (mid << ps.lo_tile_log) | lo_l;
+      uint32_t i1 = i0 + (1u << (log_dm + ps.lo_tile_log));
+      uint32_t e = ((mid_low << ps.s_log) + lo0 + lo_l) << shift;
+      El x, y, w;
+      tile_load(x, sm, E, i0);
+      tile_load(y, sm, E, i1);
+      if (DIT) {
+        if (e) {
+          load16(w, tw + e);
+          Fr::mul(y, y, w);
+        }
+        El t;
+        Fr::add(t, x, y);
+        Fr::sub(y, x, y);
+        tile_store(sm, E, i0, t);
+        tile_store(sm, E, i1, y);
+      } else {
+        El t;
+        Fr::add(t, x, y);
+        Fr::sub(y, x, y);
+        if (e) {
+          load16(w, tw + e);
+          Fr::mul(y, y, w);
+        }
+        tile_store(sm, E, i0, t);
+        tile_store(sm, E, i1, y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // One pass.  If in_b != nullptr the load computes (data[i] * in_b[i] - in_c[i]) * den  (quotient).
 template <class Fr, bool DIT>
 __global__ void __launch_bounds__(kNttThreads)
@@ -108,46 +159,7 @@ k_ntt_pass(typename Fr::El* __restrict__ data, const typename Fr::El* __restrict
   __syncthreads();
 
   // ---- butterflies
-  const uint32_t half = E >> 1;
-  for (int j = 0; j < ps.logr; j++) {
-    const int log_dm = DIT ? j : (ps.logr - 1 - j);
-    const int shift = ps.logn - 1 - ps.s_log - log_dm;   // twiddle exponent scale: d * 2^shift = n/2
-    const uint32_t dm_mask = (1u << log_dm) - 1u;
-    for (uint32_t q = threadIdx.x; q < half; q += kNttThreads) {
-      uint32_t lo_l = q & lo_mask;
-      uint32_t u = q >> ps.lo_tile_log;
-      uint32_t mid_low = u & dm_mask;
-      uint32_t mid = ((u >> log_dm) << (log_dm + 1)) | mid_low;
-      uint32_t i0 = (mid << ps.lo_tile_log) | lo_l;
-      uint32_t i1 = i0 + (1u << (log_dm + ps.lo_tile_log));
-      uint32_t e = ((mid_low << ps.s_log) + lo0 + lo_l) << shift;
-      El x, y, w;
-      tile_load(x, sm, E, i0);
-      tile_load(y, sm, E, i1);
-      if (DIT) {
-        if (e) {
-          load16(w, tw + e);
-          Fr::mul(y, y, w);
-        }
-        El t;
-        Fr::add(t, x, y);
-        Fr::sub(y, x, y);
-        tile_store(sm, E, i0, t);
-        tile_store(sm, E, i1, y);
-      } else {
-        El t;
-        Fr::add(t, x, y);
-        Fr::sub(y, x, y);
-        if (e) {
-          load16(w, tw + e);
-          Fr::mul(y, y, w);
-        }
-        tile_store(sm, E, i0, t);
-        tile_store(sm, E, i1, y);
-      }
-    }
-    __syncthreads();
-  }
+  ntt_tile_levels<Fr, DIT>(sm, ps, tw, lo0);
 
   // ---- store (+ fused scaling)
   for (uint32_t l = threadIdx.x; l < E; l += kNttThreads) {
@@ -157,6 +169,98 @@ k_ntt_pass(typename Fr::El* __restrict__ data, const typename Fr::El* __restrict
     tile_load(x, sm, E, l);
     ntt_apply_scale<Fr>(x, post, (uint32_t)gi, ps.logn);
     store16(data + gi, x);
+  }
+}
+
+// Fused middle of "interpolate, then evaluate on the coset" (the quotient does it for a, b and c): the LAST pass of the
+// unscaled inverse DIF transform and the FIRST pass of the coset DIT transform both work on the same contiguous tile
+// of 2^lc elements, so the tile makes one round trip through shared memory instead of two through HBM:
+// lc DIF levels (omega^-1 twiddles), the coset / 1/n scaling (bit-reversed exponent), lc DIT levels (omega twiddles).
+template <class Fr>
+__global__ void __launch_bounds__(kNttThreads)
+k_ntt_fused_mid(typename Fr::El* __restrict__ data, const typename Fr::El* __restrict__ tw_inv,
+                const typename Fr::El* __restrict__ tw_fwd, NttPass ps, NttScale scale) {
+  using El = typename Fr::El;
+  extern __shared__ uint4 sm[];
+  const uint32_t E = 1u << ps.logr;                   // contiguous pass: s_log = 0, lo_tile_log = 0
+  const uint64_t base = (uint64_t)blockIdx.x << ps.logr;
+  for (uint32_t l = threadIdx.x; l < E; l += blockDim.x) {
+    El x;
+    load16_rw(x, data + base + l);
+    tile_store(sm, E, l, x);
+  }
+  __syncthreads();
+  ntt_tile_levels<Fr, false>(sm, ps, tw_inv, 0);
+  for (uint32_t l = threadIdx.x; l < E; l += blockDim.x) {
+    El x;
+    tile_load(x, sm, E, l);
+    ntt_apply_scale<Fr>(x, scale, (uint32_t)(base + l), ps.logn);
+    tile_store(sm, E, l, x);
+  }
+  __syncthreads();
+  ntt_tile_levels<Fr, true>(sm, ps, tw_fwd, 0);
+  for (uint32_t l = threadIdx.x; l < E; l += blockDim.x) {
+    El x;
+    tile_load(x, sm, E, l);
+    store16(data + base + l, x);
+  }
+}
+
+// Fused end of the quotient: the LAST (strided) pass of the three coset DIT transforms, the pointwise
+// (a * b - c) / (g^n - 1) and the FIRST (strided) pass of the inverse coset DIF transform all address the same tile
+// geometry.  Three tiles live in shared memory (192 KB for 32-byte elements); only `a` is written back.
+constexpr int kNttQuotThreads = 512;
+template <class Fr>
+__global__ void __launch_bounds__(kNttQuotThreads)
+k_ntt_fused_quot(typename Fr::El* __restrict__ a, const typename Fr::El* __restrict__ b,
+                 const typename Fr::El* __restrict__ c, const typename Fr::El* __restrict__ tw_fwd,
+                 const typename Fr::El* __restrict__ tw_inv, NttPass ps, const typename Fr::El* __restrict__ den) {
+  using El = typename Fr::El;
+  extern __shared__ uint4 sm[];
+  const int elog = ps.logr + ps.lo_tile_log;
+  const uint32_t E = 1u << elog;
+  const uint32_t chunks = sizeof(El) / 16;
+  uint4* ta = sm;
+  uint4* tb = sm + (size_t)chunks * E;
+  uint4* tc = tb + (size_t)chunks * E;
+  const uint32_t lo_mask = (1u << ps.lo_tile_log) - 1u;
+  const uint32_t tiles_per_hi = 1u << (ps.s_log - ps.lo_tile_log);
+  const uint32_t hi = blockIdx.x / tiles_per_hi;
+  const uint32_t lo0 = (blockIdx.x % tiles_per_hi) << ps.lo_tile_log;
+  const uint64_t base = ((uint64_t)hi << (ps.s_log + ps.logr)) + lo0;
+  for (uint32_t l = threadIdx.x; l < E; l += blockDim.x) {
+    const uint64_t gi = base + ((uint64_t)(l >> ps.lo_tile_log) << ps.s_log) + (l & lo_mask);
+    El x;
+    load16_rw(x, a + gi);
+    tile_store(ta, E, l, x);
+    load16(x, b + gi);
+    tile_store(tb, E, l, x);
+    load16(x, c + gi);
+    tile_store(tc, E, l, x);
+  }
+  __syncthreads();
+  ntt_tile_levels<Fr, true>(ta, ps, tw_fwd, lo0);
+  ntt_tile_levels<Fr, true>(tb, ps, tw_fwd, lo0);
+  ntt_tile_levels<Fr, true>(tc, ps, tw_fwd, lo0);
+  El d;
+  load16(d, den);
+  for (uint32_t l = threadIdx.x; l < E; l += blockDim.x) {
+    El x, y, z;
+    tile_load(x, ta, E, l);
+    tile_load(y, tb, E, l);
+    tile_load(z, tc, E, l);
+    Fr::mul(x, x, y);
+    Fr::sub(x, x, z);
+    Fr::mul(x, x, d);
+    tile_store(ta, E, l, x);
+  }
+  __syncthreads();
+  ntt_tile_levels<Fr, false>(ta, ps, tw_inv, lo0);
+  for (uint32_t l = threadIdx.x; l < E; l += blockDim.x) {
+    const uint64_t gi = base + ((uint64_t)(l >> ps.lo_tile_log) << ps.s_log) + (l & lo_mask);
+    El x;
+    tile_load(x, ta, E, l);
+    store16(a + gi, x);
   }
 }
 

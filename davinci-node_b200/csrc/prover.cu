@@ -231,7 +231,9 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
       auto set_bytes = [&](uint64_t npts, size_t pb, int c) {
         return (uint64_t)msm_ntables(msm_nwin(bits, c), ts) * std::max<uint64_t>(npts, 1) * pb;
       };
-      const int cw = cb->table_window(wire_pts, ts), cz = cb->table_window(std::max<uint64_t>(d.g1_Z.len, 1), ts);
+      int cw = cb->table_window(wire_pts, ts);
+      if (cw >= 18) cw = std::max(17, cw - 2);     // sparse-witness adjustment, as below
+      const int cz = cb->table_window(std::max<uint64_t>(d.g1_Z.len, 1), ts);
       uint64_t parts[6] = {set_bytes(d.g1_A.len + 2, g1b, cw), set_bytes(d.g1_B.len + 2, g1b, cw),
                            set_bytes(d.g2_B.len + 2, g2b, cw), set_bytes(d.g1_K.len + 1, g1b, cw),
                            set_bytes(d.g1_Z.len, g1b, cz),
@@ -277,7 +279,13 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
       B200_CUDA(cudaStreamSynchronize(s));   // staging buffer is reused by the next base set
     };
     // the wire-indexed keys share one digit/sort pass per proof, hence one window width
+    // The cost model assumes dense scalars; a solved witness is sparse (40% zeros, 20% ones, 25% below
+    // 2^64), so the wire-indexed sets fill ~3 digits per scalar and their bucket reduction weighs far more than the
+    // model thinks.  Measured on the 2^22 voteverifier shape: c = 20 / 19 / 18 / 17 / 16 -> 17.3 / 17.5 / 18.3 / 17.9 /
+    // 14.5 proofs/s (and 8.1 -> 7.7 proofs/s for a uniform-random wire vector at c = 18): two bits below the model,
+    // but never so few buckets that the one-thread-per-bucket accumulation runs out of threads.
     int cw = cb->table_window(wire_pts, ts);
+    if (cw >= 18) cw = std::max(17, cw - 2);
     if (const char* e = std::getenv("B200_WIRE_WINDOW")) {   // tuning knob: window width of the wire-indexed keys
       if (std::atoi(e) >= 4 && std::atoi(e) <= 22) cw = std::atoi(e);
     }
@@ -460,11 +468,9 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
     prof_end(tok_mul, sh);
   }
 
-  // ---- quotient, Z MSM, proof of knowledge
+  // ---- proof of knowledge, quotient, Z MSM.  The (small) PoK MSM goes first: its latency-bound tail then hides behind
+  //      the quotient and the Z accumulation instead of ending the proof
   B200_CUDA(cudaStreamWaitEvent(sb, S.ev[1], 0));
-  if (in.abc_form == 1) cb->compute_h_tail(I.dom, a, b, c, sb);
-  else cb->compute_h(I.dom, a, b, c, sb);
-  cb->msm(1, nullptr, a + z_offset * frb, nZ, o_z, S.ws[0], sb, 0, nullptr, nullptr, &I.tZ, false);
   if (have_pok) {
     // segment i of the committed values is scaled by challenge^i: scale every later segment once per step
     uint64_t off = 0;
@@ -474,6 +480,9 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
     }
     cb->msm(1, nullptr, cv, total_commit, o_pok, S.ws[3], sb, 0, nullptr, nullptr, &I.tSigma, false);
   }
+  if (in.abc_form == 1) cb->compute_h_tail(I.dom, a, b, c, sb);
+  else cb->compute_h(I.dom, a, b, c, sb);
+  cb->msm(1, nullptr, a + z_offset * frb, nZ, o_z, S.ws[0], sb, 0, nullptr, nullptr, &I.tZ, false);
   // ---- join every tail on the high-priority stream
   S.ws[0].wait_tail(sh);
   S.ws[1].wait_tail(sh);

@@ -251,7 +251,7 @@ B200_API int b200_profile_collect(double ms_out[5], uint64_t count_out[5]);
 B200_API int b200_profile_timeline(double* out, uint64_t cap_records, uint64_t* n_out);
 
 /* ---- debug / parity entry points (device pointers; element-wise over n items) ---------------
- * field: 0 = Fp, 1 = Fr, 2 = Fp2 ; op: 0 add, 1 sub, 2 mul, 3 sqr, 4 from_mont, 5 to_mont, 6 inv, 7 neg, 8 sqrt (zero when not a square) */
+ * field: 0 = Fp, 1 = Fr, 2 = Fp2 ; op: 0 add, 1 sub, 2 mul, 3 sqr, 4 from_mont, 5 to_mont, 6 inv, 7 neg, 8 sqrt (zero when not a square), 9 inversion by binary GCD */
 B200_API int b200_dbg_field_op_dev(int curve, int field, int op, const void* d_a, const void* d_b, void* d_out, uint64_t n,
                           void* cuda_stream);
 /* op: 0 madd (xyzz += affine), 1 add (xyzz += xyzz), 2 dbl, 3 to_affine, 4 mul by Fr scalar */

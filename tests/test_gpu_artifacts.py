@@ -148,3 +148,21 @@ def test_proving_key_stream_roundtrip_and_prove(env, cname):
         art.read_proving_key(stream[:-3], L.id)
     with pytest.raises(art.ArtifactError):
         art.read_proving_key(stream + b"\x00", L.id)
+
+
+@pytest.mark.parametrize("cname", CURVES)
+def test_binary_gcd_inversion(env, cname):
+    """FpT::inv_bin (the one-thread inversion of the proof's final affine normalisation) == a^-1, with 0 -> 0."""
+    import torch
+    art, capi, layout = env
+    cx = OC.ctx(cname)
+    L = layout.Layout(cname)
+    rnd = random.Random(9)
+    p = cx.p
+    vals = [0, 1, 2, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2] + [rnd.randrange(p) for _ in range(40)] + [1 << k for k in (31, 32, 63, 64, 200)]
+    d = torch.from_numpy(L.enc_fp(vals)).cuda()
+    out = torch.empty_like(d)
+    capi.check(capi.lib.b200_dbg_field_op_dev(L.id, 0, 9, d.data_ptr(), None, out.data_ptr(), len(vals),
+                                              torch.cuda.current_stream().cuda_stream))
+    got = L.dec_fp(out.cpu().numpy())
+    assert got == [pow(v, -1, p) if v else 0 for v in vals]
