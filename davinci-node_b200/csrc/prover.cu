@@ -226,16 +226,46 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
     //      largest table build) fit the key's budget.  Budget: b200_set_pk_table_budget / B200_PK_BUDGET_GB, else
     //      55% of the memory free right now minus this key's proof workspaces.
     const uint64_t wire_pts = std::max({d.g1_A.len + 2, d.g1_B.len + 2, d.g1_K.len + 1});
+    // Window of the wire-indexed keys (they share one digit / sort pass per proof, hence one width).
+    // The cost model assumes dense scalars; a solved witness is sparse (SURVEY.md 8d: 40% zeros, 20% ones, 25% below
+    // 2^64), so the wire-indexed sets fill ~3 digits per scalar and their bucket reduction weighs far more than the
+    // model thinks.  Measured on the 2^22 voteverifier shape, 4 proofs in flight: c = 20 / 19 / 18 / 17 / 16 -> 17.3 /
+    // 17.5 / 18.3 / 17.9 / 14.5 proofs/s (and 8.1 -> 7.7 proofs/s for a uniform-random wire vector at c = 18): two
+    // bits below the model, but never so few buckets that the one-thread-per-bucket accumulation runs out of threads.
+    // A range-split slice (its Z set covers at most half the domain) is proved one at a time, nothing overlaps its
+    // MSMs, and the narrower window starves the G2 accumulation: slices keep the model's window (measured on the
+    // BW6-761 2^22 aggregator shape: N = 2 / 4 slices 135.8 / 80.9 ms with the model's window, 172.5 / 98.2 ms two
+    // bits below it).
+    const bool slice_key = d.g1_Z.len * 2 <= d.domain_size;
+    auto wire_window = [&](int ts) {
+      int cw = cb->table_window(wire_pts, ts);
+      if (!slice_key && cw >= 18) cw = std::max(17, cw - 2);
+      if (const char* e = std::getenv("B200_WIRE_WINDOW")) {   // tuning knob
+        if (std::atoi(e) >= 4 && std::atoi(e) <= 22) cw = std::atoi(e);
+      }
+      return cw;
+    };
+    // G2 re-uses B1's digit / sort pass (same wire map), so it shares the wire window by default.  B200_G2_WINDOW=model
+    // (or a width) gives it its own window and its own sort pass: a single proof run alone finishes sooner (2^22
+    // voteverifier: 67 -> 58.4 ms, the G2 accumulation no longer starves: ncu 34% -> 82% multiplier pipe) but with
+    // four proofs in flight the extra sort costs throughput (18.24 -> 17.50 proofs/s), so it is opt-in.
+    auto g2_window = [&](int ts, int cw) {
+      if (const char* e = std::getenv("B200_G2_WINDOW")) {
+        if (!std::strcmp(e, "model")) return cb->table_window(d.g2_B.len + 2, ts);
+        if (std::atoi(e) >= 4 && std::atoi(e) <= 22) return std::atoi(e);
+      }
+      return cw;
+    };
     auto tables_bytes = [&](int ts, uint64_t* peak) {
       const int bits = cb->fr_bits();
       auto set_bytes = [&](uint64_t npts, size_t pb, int c) {
         return (uint64_t)msm_ntables(msm_nwin(bits, c), ts) * std::max<uint64_t>(npts, 1) * pb;
       };
-      int cw = cb->table_window(wire_pts, ts);
-      if (cw >= 18) cw = std::max(17, cw - 2);     // sparse-witness adjustment, as below
+      const int cw = wire_window(ts);
       const int cz = cb->table_window(std::max<uint64_t>(d.g1_Z.len, 1), ts);
       uint64_t parts[6] = {set_bytes(d.g1_A.len + 2, g1b, cw), set_bytes(d.g1_B.len + 2, g1b, cw),
-                           set_bytes(d.g2_B.len + 2, g2b, cw), set_bytes(d.g1_K.len + 1, g1b, cw),
+                           set_bytes(d.g2_B.len + 2, g2b, g2_window(ts, cw)),
+                           set_bytes(d.g1_K.len + 1, g1b, cw),
                            set_bytes(d.g1_Z.len, g1b, cz),
                            2 * set_bytes(total_sigma, g1b, cb->table_window(std::max<uint64_t>(total_sigma, 1), ts))};
       uint64_t sum = 0, big = 0;
@@ -278,20 +308,11 @@ std::unique_ptr<ProvingKeyDev> ProvingKeyDev::create(const b200_pk_desc& d, cons
       in->table_bytes += (uint64_t)t.ntab * std::max<uint64_t>(cnt, 1) * pb;
       B200_CUDA(cudaStreamSynchronize(s));   // staging buffer is reused by the next base set
     };
-    // the wire-indexed keys share one digit/sort pass per proof, hence one window width
-    // The cost model assumes dense scalars; a solved witness is sparse (SURVEY.md 8d: 40% zeros, 20% ones, 25% below
-    // 2^64), so the wire-indexed sets fill ~3 digits per scalar and their bucket reduction weighs far more than the
-    // model thinks.  Measured on the 2^22 voteverifier shape: c = 20 / 19 / 18 / 17 / 16 -> 17.3 / 17.5 / 18.3 / 17.9 /
-    // 14.5 proofs/s (and 8.1 -> 7.7 proofs/s for a uniform-random wire vector at c = 18): two bits below the model,
-    // but never so few buckets that the one-thread-per-bucket accumulation runs out of threads.
-    int cw = cb->table_window(wire_pts, ts);
-    if (cw >= 18) cw = std::max(17, cw - 2);
-    if (const char* e = std::getenv("B200_WIRE_WINDOW")) {   // tuning knob: window width of the wire-indexed keys
-      if (std::atoi(e) >= 4 && std::atoi(e) <= 22) cw = std::atoi(e);
-    }
+    const int cw = wire_window(ts);
     put_tables(in->tA, 1, d.g1_A, g1b, d.g1_delta, d.g1_alpha, cw);
     put_tables(in->tB1, 1, d.g1_B, g1b, d.g1_delta, d.g1_beta, cw);
-    put_tables(in->tB2, 2, d.g2_B, g2b, d.g2_delta, d.g2_beta, cw);
+    const int cw2 = g2_window(ts, cw);
+    put_tables(in->tB2, 2, d.g2_B, g2b, d.g2_delta, d.g2_beta, cw2);
     put_tables(in->tK, 1, d.g1_K, g1b, d.g1_delta, nullptr, cw);
     put_tables(in->tZ, 1, d.g1_Z, g1b, nullptr, nullptr);
     upload(in->mapA, mapA.data(), mapA.size() * 4, s);
@@ -447,8 +468,12 @@ void ProvingKeyDev::prove(const b200_prove_in& in, const b200_proof_out& out, in
       B200_CUDA(cudaStreamWaitEvent(sg, S.ev[2], 0));
     }
     cb->msm_reduce(1, so, 0, 3, sets, o_ar, S.ws[1], sw, false);   // -> o_ar, o_bs1, o_k (contiguous)
-    const MsmBases* g2set[1] = {&I.tB2};
-    cb->msm_reduce(2, so, 1, 1, g2set, o_bs2, S.ws[2], sg, false);
+    if (I.tB2.c == I.tB1.c && I.tB2.tstride == I.tB1.tstride) {
+      const MsmBases* g2set[1] = {&I.tB2};
+      cb->msm_reduce(2, so, 1, 1, g2set, o_bs2, S.ws[2], sg, false);
+    } else {
+      cb->msm(2, nullptr, W, m + 4, o_bs2, S.ws[2], sg, 0, nullptr, (const uint32_t*)I.mapB.p, &I.tB2, false);
+    }
   }
   // s*Ar and r*Bs1 (two single-thread scalar multiplications, 1.4 ms on BLS12-377, 10 ms on BW6-761) only need the
   // wire-indexed G1 sums: they run on the high-priority stream as soon as that tail is done, long before the quotient MSM

@@ -60,13 +60,21 @@ def launches(path, out, title):
         fh.write("\nTotal kernel time: %.3f ms over %d launches.\n" % (tot, sum(a[0] for a in agg.values())))
 
 
-def full(path, out, title):
+def _raw_rows(path):
+    """rows of `ncu --page raw --csv`: from a report, or from a CSV already exported on the GPU box (reports with
+    --import-source exceed what gpurun copies back)"""
+    if path.endswith(".csv"):
+        return list(csv.reader(open(path)))
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    return list(csv.reader(raw.splitlines()))
+
+
+def full(path, out, title):
+    rows = _raw_rows(path)
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     with open(out, "w") as fh:
-        fh.write("# %s\n\nSource: `%s` (ncu --set full --clock-control none --import-source on).\n\n" % (title, path))
+        fh.write("# %s\n\nSource: `%s` (ncu --set full --clock-control none).\n\n" % (title, path))
         for r in rows[2:]:
             fh.write("## `%s`\n\n| metric | value | unit |\n|---|---:|---|\n" % r[idx["Kernel Name"]].split("(")[0][:120])
             for k in KEYS:
@@ -82,8 +90,7 @@ FACT_PATTERNS = {"k_msm_accumulate_g1": ("k_msm_accumulate<", "FpT<"), "k_msm_ac
 def facts(path, out, specs):
     import json
     import os
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+    rows = _raw_rows(path)
     hdr = rows[0]
     idx = {h: i for i, h in enumerate(hdr)}
     res = json.load(open(out)) if os.path.exists(out) else {}

@@ -76,10 +76,10 @@ def main():
             for grp in (1, 2):
                 w = L.coord_width(grp)
                 pb = 2 * w * L.fp_bytes
-                if n * pb > 20e9:                            # the points alone: keep the sweep inside one GPU
+                if n * pb > 9e9:                             # keep points + sort workspaces inside one GPU
                     continue
                 # table mode needs ~13 tables plus 1.5x that as transient build scratch
-                with_tables = n * pb * 13 * 2.6 < 150e9
+                with_tables = n * pb * 13 * 2.6 < 90e9
                 pts = torch.from_numpy(synthetic.rand_canonical(rng, n * 2 * w, L.fp_l, L.p.bit_length()).view(np.uint8).reshape(-1)).cuda()
                 out = torch.zeros(L.xyzz_bytes(grp), dtype=torch.uint8, device="cuda")
                 wms = timed(lambda: capi.check(lib.b200_msm_dev(L.id, grp, pts.data_ptr(), sc.data_ptr(), n, out.data_ptr(), 0, st)), 2)
