@@ -553,18 +553,20 @@ def roofline_detail(torch, capi, lib, synthetic, np, wl, sol, logn, info, ms_ste
                 "kernel_frac_note": "the %d x %d x (1 - 2^-%d) mixed additions the kernel really performs, over the kernel's own "
                                     "duration" % (nZ, nwin_z, cz),
                 "peak_source": peak_note, "frac_of_nominal": g1_alg / (g1_total_ms / 1e3) / peak_nominal,
-                "traffic": (fz["dram_bytes"] * nZ / fz["points"]) if fz else None,
-                "traffic_source": ("%s (ncu --set full, %d points, scaled by point count)" % (facts_src, fz["points"])) if fz else None,
+                "traffic": (fz["dram_bytes"] * (nZ * nwin_z * (1 - 2.0 ** -cz)) / fz["adds"]) if fz else None,
+                "traffic_source": ("%s (ncu --set full of the kernel inside one proof: %d mixed additions at c=%d, scaled by "
+                                   "the additions of this launch)" % (facts_src, fz["adds"], fz["window_bits"])) if fz else None,
                 "ncu_pipe_fmaheavy_pct": fz.get("fmaheavy_pct") if fz else None,
                 "algorithmic_point_bytes": BW.msm_adds_star(nZ, bits) * L.affine_bytes(1),
                 "launch_ms": g1_total_ms, "kernel_ms": g1_acc_ms, "algorithmic_macs_per_launch": g1_alg}
     f2 = facts.get("k_msm_accumulate_g2", {})
+    g2_c, g2_nwin = cz, nwin_z     # the model's window of this set is taken to be the Z set's (same order of magnitude of points)
     roofline_g2 = {"bound": "imad", "kernel": "G2 MSM (Bs), %d points, uniform scalars (k_msm_accumulate<G2> = %.0f%% of it)" % (nB, 100 * g2_acc_ms / g2_total_ms),
                    "achieved": g2_alg / (g2_total_ms / 1e3) / 1e12, "peak": peak_meas / 1e12,
                    "unit": "T wide-MAC/s (32x32->64 IMAD.WIDE)", "frac": g2_alg / (g2_total_ms / 1e3) / peak_meas,
                    "peak_source": peak_note, "frac_of_nominal": g2_alg / (g2_total_ms / 1e3) / peak_nominal,
-                   "traffic": (f2["dram_bytes"] * nB / f2["points"]) if f2 else None,
-                   "traffic_source": facts_src if f2 else None,
+                   "traffic": (f2["dram_bytes"] * (nB * g2_nwin * (1 - 2.0 ** -g2_c)) / f2["adds"]) if f2 else None,
+                   "traffic_source": ("%s (scaled by additions; includes the kernel's spill stores)" % facts_src) if f2 else None,
                    "launch_ms": g2_total_ms, "kernel_ms": g2_acc_ms, "algorithmic_macs_per_launch": g2_alg}
     # NTT passes alone
     ms = (C.c_double * 5)()

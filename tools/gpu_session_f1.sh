@@ -1,3 +1,2 @@
 cd $GRAFT_REPO_ROOT
-O=gpurun_out
-timeout 80 python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node 2 --master-port 29611 bench.py --gpus 2 --config aggregator --mode range-split --steps 4 --warmup 2 > $O/r2k_agg_n2.json 2> $O/r2k_agg_n2.err; cut -c1-250 $O/r2k_agg_n2.json; tail -c 300 $O/r2k_agg_n2.err
+timeout 80 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2l_bench_n1.json 2> gpurun_out/r2l_bench.err; cut -c1-120 gpurun_out/r2l_bench_n1.json; tail -c 300 gpurun_out/r2l_bench.err
