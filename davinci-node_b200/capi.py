@@ -69,6 +69,8 @@ _PROTOS = {
     "b200_compressed_bytes": (_u64, [_i, _i]),
     "b200_points_decompress_dev": (_i, [_i, _i, _vp, _u64, _vp, _vp, _vp]),
     "b200_points_compress_dev": (_i, [_i, _i, _vp, _u64, _vp, _vp]),
+    "b200_gt_bytes": (_u64, [_i]),
+    "b200_pairing_check": (_i, [_i, _vp, _vp, _u32, C.POINTER(_i), _vp, _i]),
     "b200_fixed_base_dev": (_i, [_i, _i, _vp, _vp, _u64, _vp, _vp]),
     "b200_bases_create_dev": (_i, [_i, _i, _vp, _u64, _i, C.POINTER(_u64), _vp]),
     "b200_bases_release": (_i, [_u64]),

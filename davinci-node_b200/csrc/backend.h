@@ -219,6 +219,12 @@ struct CurveBackend {
   virtual size_t compressed_bytes(int group) const = 0;
   virtual void points_decompress(int group, const void* d_bytes, void* d_affine, uint64_t n, uint32_t* d_err, cudaStream_t s) = 0;
   virtual void points_compress(int group, const void* d_affine, void* d_bytes, uint64_t n, cudaStream_t s) = 0;
+  // product-of-pairings check (pairing.cuh): d_g1 / d_g2 = n affine points each; d_f = n * gt_bytes() scratch for the
+  // Miller values, d_gt = the reduced pairing of the product, d_flags[0..n) = 1 where P_i is outside the order-r subgroup,
+  // d_flags[n] = 1 when the product is one
+  virtual size_t gt_bytes() const = 0;
+  virtual void pairing_check(const void* d_g1, const void* d_g2, uint32_t n, void* d_f, void* d_gt, uint32_t* d_flags,
+                             cudaStream_t s) = 0;
   virtual void blob_to_scalars(const void* d_blob, void* d_scalars, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;
   // KZG opening (EIP-4844 compute_kzg_proof_impl): roots = w^brp(i) table; kzg_open turns the blob's scalars p and
   // the point z (32 big-endian bytes on the device) into the quotient evaluations q and y = p(z) (32 bytes).

@@ -520,6 +520,36 @@ int b200_blob_proof(uint64_t h, const uint8_t* blob, const uint8_t point_be[32],
   });
 }
 
+// ---------------------------------------------------------------------------------- pairing check
+uint64_t b200_gt_bytes(int c) { return backend_by_id(c) ? backend_by_id(c)->gt_bytes() : 0; }
+
+int b200_pairing_check(int curve_id, const void* g1, const void* g2, uint32_t n, int* result_out, void* gt_out, int device) {
+  return guarded([&] {
+    CurveBackend& cb = curve(curve_id);
+    if (!result_out) throw std::runtime_error("result_out is null");
+    if (n && (!g1 || !g2)) throw std::runtime_error("null input with n > 0");
+    if (n > 64) throw std::runtime_error("pairing check: at most 64 pairs");
+    DeviceGuard dg(device);
+    ScopedStream st;
+    const size_t b1 = cb.affine_bytes(1), b2 = cb.affine_bytes(2), gb = cb.gt_bytes();
+    ScopedDev d1(n * b1), d2(n * b2), df(n * gb), dgt(gb), dfl((n + 1) * sizeof(uint32_t));
+    if (n) {
+      B200_CUDA(cudaMemcpyAsync(d1.p, g1, n * b1, cudaMemcpyHostToDevice, st.s));
+      B200_CUDA(cudaMemcpyAsync(d2.p, g2, n * b2, cudaMemcpyHostToDevice, st.s));
+    }
+    B200_CUDA(cudaMemsetAsync(dfl.p, 0, (n + 1) * sizeof(uint32_t), st.s));
+    cb.pairing_check(d1.p, d2.p, n, df.p, dgt.p, (uint32_t*)dfl.p, st.s);
+    std::vector<uint32_t> flags(n + 1);
+    B200_CUDA(cudaMemcpyAsync(flags.data(), dfl.p, (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st.s));
+    if (gt_out) B200_CUDA(cudaMemcpyAsync(gt_out, dgt.p, gb, cudaMemcpyDeviceToHost, st.s));
+    B200_CUDA(cudaStreamSynchronize(st.s));
+    for (uint32_t i = 0; i < n; i++) {
+      if (flags[i]) throw std::runtime_error("pairing check: G1 point " + std::to_string(i) + " is not in the order-r subgroup");
+    }
+    *result_out = flags[n] ? 1 : 0;
+  });
+}
+
 // ---------------------------------------------------------------------------------- key artefacts
 uint64_t b200_compressed_bytes(int c, int g) { return backend_by_id(c) && (g == 1 || g == 2) ? backend_by_id(c)->compressed_bytes(g) : 0; }
 

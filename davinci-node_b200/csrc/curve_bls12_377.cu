@@ -10,6 +10,7 @@ struct Cfg_bls12_377 {
   using Fr = FpT<bls12_377_fr>;
   using G1F = Fp;
   using G2F = Fp2T<bls12_377_fp, 5>;
+  using Tower = pairing_bls12_377;        // extension-field shape of the pairing (pairing.cuh)
   static constexpr int FLAG_BITS = 3;   // gnark-crypto point-compression flag bits (serde.cuh)
   // E: y^2 = x^3 + 1 ; D-twist E': y^2 = x^3 + 1/u
   static __device__ void curve_b(typename G1F::El& b1, typename G2F::El& b2) {

@@ -10,6 +10,7 @@ struct Cfg_bls12_381 {
   using Fr = FpT<bls12_381_fr>;
   using G1F = Fp;
   using G2F = Fp2T<bls12_381_fp, 1>;
+  using Tower = pairing_bls12_381;        // extension-field shape of the pairing (pairing.cuh)
   static constexpr int FLAG_BITS = 3;   // gnark-crypto point-compression flag bits (serde.cuh)
   // E: y^2 = x^3 + 4 ; M-twist E': y^2 = x^3 + 4(1+u)
   static __device__ void curve_b(typename G1F::El& b1, typename G2F::El& b2) {

@@ -10,6 +10,7 @@ struct Cfg_bn254 {
   using Fr = FpT<bn254_fr>;
   using G1F = Fp;
   using G2F = Fp2T<bn254_fp, 1>;
+  using Tower = pairing_bn254;        // extension-field shape of the pairing (pairing.cuh)
   static constexpr int FLAG_BITS = 2;   // gnark-crypto point-compression flag bits (serde.cuh)
   // E: y^2 = x^3 + 3 ; D-twist E': y^2 = x^3 + 3/(9+u)
   static __device__ void curve_b(typename G1F::El& b1, typename G2F::El& b2) {

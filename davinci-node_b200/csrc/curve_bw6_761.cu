@@ -10,6 +10,7 @@ struct Cfg_bw6_761 {
   using Fr = FpT<bw6_761_fr>;
   using G1F = Fp;
   using G2F = FpT<bw6_761_fp>;
+  using Tower = pairing_bw6_761;        // extension-field shape of the pairing (pairing.cuh)
   static constexpr int FLAG_BITS = 3;   // gnark-crypto point-compression flag bits (serde.cuh)
   // E: y^2 = x^3 - 1 ; M-twist E' (over Fp): y^2 = x^3 + 4
   static __device__ void curve_b(typename G1F::El& b1, typename G2F::El& b2) {

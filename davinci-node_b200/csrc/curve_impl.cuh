@@ -10,6 +10,7 @@
 #include "ntt.cuh"
 #include "kzg.cuh"
 #include "serde.cuh"
+#include "pairing.cuh"
 #include <memory>
 #include <map>
 #include <mutex>
@@ -503,6 +504,39 @@ void msm_set_smem_attrs() {
 }
 
 // ------------------------------------------------------------------------------------ backend
+// ------------------------------------------------------------------------------------ pairing check (pairing.cuh)
+template <class Cfg>
+using PairOf = PairingT<typename Cfg::Fp, typename Cfg::Tower, typename Cfg::Fr::Params>;
+
+// One pairing per block, one thread: the Miller value of (P_i, Q_i).  flags[i] = 1 when r * P_i != infinity.
+template <class Cfg>
+__global__ void k_pairing_miller(const typename Cfg::Fp::El* g1, const typename Cfg::Fp::El* g2, uint32_t n,
+                                 typename PairOf<Cfg>::Ext* f_out, uint32_t* flags) {
+  using PT = PairOf<Cfg>;
+  const uint32_t i = blockIdx.x;
+  if (threadIdx.x != 0 || i >= n) return;
+  typename PT::Ext f;
+  const bool in_subgroup = PT::miller(f, g1 + 2 * (size_t)i, g2 + 2 * PT::NQ * (size_t)i);
+  f_out[i] = f;
+  flags[i] = in_subgroup ? 0u : 1u;
+}
+// One thread: product of the Miller values, final exponentiation, comparison with one.
+template <class Cfg>
+__global__ void k_pairing_finish(const typename PairOf<Cfg>::Ext* f, uint32_t n, typename PairOf<Cfg>::Ext* gt_out,
+                                 uint32_t* is_one) {
+  using PT = PairOf<Cfg>;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  typename PT::Ext acc, g;
+  PT::ext_one(acc);
+  for (uint32_t i = 0; i < n; i++) {
+    g = f[i];
+    PT::ext_mul(acc, acc, g);
+  }
+  PT::final_exp(g, acc);
+  *gt_out = g;
+  *is_one = PT::ext_is_one(g) ? 1u : 0u;
+}
+
 template <class Cfg>
 struct CurveImpl : CurveBackend {
   using Fp = typename Cfg::Fp;
@@ -844,6 +878,19 @@ struct CurveImpl : CurveBackend {
     prof_count_launches(1);
     B200_CUDA(cudaGetLastError());
   }
+  size_t gt_bytes() const override { return sizeof(typename PairOf<Cfg>::Ext); }
+  void pairing_check(const void* d_g1, const void* d_g2, uint32_t n, void* d_f, void* d_gt, uint32_t* d_flags,
+                     cudaStream_t s) override {
+    using Ext = typename PairOf<Cfg>::Ext;
+    if (n) {
+      k_pairing_miller<Cfg><<<n, 1, 0, s>>>((const typename Fp::El*)d_g1, (const typename Fp::El*)d_g2, n, (Ext*)d_f, d_flags);
+      B200_CUDA(cudaGetLastError());
+    }
+    k_pairing_finish<Cfg><<<1, 1, 0, s>>>((const Ext*)d_f, n, (Ext*)d_gt, d_flags + n);
+    prof_count_launches(n ? 2 : 1);
+    B200_CUDA(cudaGetLastError());
+  }
+
   void points_compress(int group, const void* d_affine, void* d_bytes, uint64_t n, cudaStream_t s) override {
     if (!n) return;
     const unsigned blocks = (unsigned)((n + 63) / 64);

@@ -147,5 +147,5 @@ def Setup(ccs: ConstraintSystem):
         infinity_a=infA, infinity_b=infB, commitment_keys=keys)
     vk = VerifyingKey(curve_id=L.id, g1_alpha=pk.g1_alpha, g1_K=fb1([Kfull[i] * ginv % q for i in pub]),
                       g2_beta=pk.g2_beta, g2_gamma=fb2([gamma]), g2_delta=pk.g2_delta, commitment_keys=vkeys,
-                      public_and_commitment_committed=[[] for _ in ccs.commitments])
+                      public_and_commitment_committed=[list(cm.get("public_committed", [])) for cm in ccs.commitments])
     return pk, vk

@@ -228,6 +228,20 @@ B200_API int b200_points_decompress_dev(int curve, int group, const void* d_byte
 B200_API int b200_points_compress_dev(int curve, int group, const void* d_affine, uint64_t n, void* d_bytes_out,
                                       void* cuda_stream);
 
+/* ---- proof verification: product-of-pairings check ----------------------------------------------------
+ * *result_out = 1 when prod_i e(P_i, Q_i) == 1, else 0.  This is the pairing check of gnark's groth16.Verify, which the
+ * reference runs right after every proof (circuits/artifacts.go:595-613: e(-Ar, Bs) e(alpha, beta) e(L, gamma) e(Krs, delta)
+ * == 1, and the Pedersen check e(C, GSigmaNeg) e(PoK, G) == 1), i.e. gnark-crypto's <curve>.PairingCheck, and of the EIP-197
+ * precompile call in config/statetransition_vkey.sol:720-746.  Points: n affine G1 / G2 points in gnark memory layout
+ * (Montgomery limbs; all-zero = infinity), HOST pointers.  The reduced Tate pairing is used (csrc/pairing.cuh): the
+ * predicate equals gnark's, the group element does not (optimal ate differs by a fixed exponent).  gt_out (optional,
+ * b200_gt_bytes(curve) bytes): the value of the product as k Fp coefficients of Fp[w]/(w^k + ...), Montgomery limbs.
+ * Fails (non-zero status) when some P_i is not in the order-r subgroup.  The caller owns the rest of Verify: the
+ * commitment challenges (hash-to-field) and the public-input MSM (b200_msm). */
+B200_API uint64_t b200_gt_bytes(int curve);
+B200_API int b200_pairing_check(int curve, const void* g1_affine, const void* g2_affine, uint32_t n, int* result_out,
+                                void* gt_out, int device);
+
 /* ---- setup building block / instrumentation -----------------------------------------------------
  * out[i] = [k_i] base as affine points: the fixed-base batch scalar multiplication groth16.Setup is
  * made of (prover/setup.go:15-28 -> groth16.Setup).  Device pointers. */

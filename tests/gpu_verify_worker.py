@@ -1,0 +1,102 @@
+"""Worker of tests/test_gpu_zz_verify.py (own process: a fault in the new pairing kernels must not poison the CUDA context
+of the rest of the GPU suite).  Prints one JSON line {"ok": true, ...} or raises."""
+import json
+import os
+import random
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+
+def main():
+    import numpy as np
+    from davinci_node_b200 import capi, gnark_types as T, layout, prover, verifier
+    from oracle import curve as OC
+    from oracle import groth16 as OG
+    from oracle import pairing
+    from oracle_bridge import ccs_from_oracle, pk_from_oracle, vk_from_oracle
+    capi.init(1)
+    out = {"pairing_ms": {}, "verify_ms": {}}
+
+    # ---- 1. the pairing itself: value bit-identical to the oracle's reduced Tate pairing, product checks, edge cases
+    for cname in ("bn254", "bls12_377", "bls12_381", "bw6_761"):
+        pr = pairing.get(cname)
+        cx = pr.cx
+        L = layout.Layout(cname)
+        a, b = 0x1234567, 0xfedcba9
+        P, Q = cx.G1.mul(cx.g1, a), cx.G2.mul(cx.g2, b)
+        e1 = lambda pt: L.enc_affine([pt], 1)
+        e2 = lambda pt: L.enc_affine([pt], 2)
+        t0 = time.time()
+        ok, gt = verifier.pairing_check(L.id, [e1(P)], [e2(Q)], want_gt=True)
+        out["pairing_ms"][cname] = round(1e3 * (time.time() - t0), 1)
+        assert gt == pr.pair(P, Q), cname + ": reduced pairing value differs from the oracle"
+        assert not ok
+        good = [(cx.G1.mul(cx.g1, a), cx.g2), (cx.G1.neg(cx.g1), cx.G2.mul(cx.g2, a))]
+        bad = [(cx.G1.mul(cx.g1, a), cx.g2), (cx.G1.neg(cx.g1), cx.G2.mul(cx.g2, a + 1))]
+        chk = lambda pairs: verifier.pairing_check(L.id, [e1(p) for p, _ in pairs], [e2(q) for _, q in pairs])
+        assert chk(good) and pr.product_is_one(good), cname
+        assert not chk(bad), cname
+        assert chk(good + [(None, cx.g2), (cx.g1, None)]), cname
+        assert chk([]), cname
+        if cname != "bn254":          # BN254's G1 has cofactor 1
+            rnd = random.Random(3)
+            while True:
+                x = rnd.randrange(cx.p)
+                y = OC.sqrt_mod((x * x * x + cx.G1.b) % cx.p, cx.p)
+                if y is not None and cx.G1.mul((x, y), cx.r) is not None:
+                    break
+            try:
+                chk([((x, y), cx.g2)])
+                raise AssertionError(cname + ": a point outside the subgroup was accepted")
+            except capi.B200Error as e:
+                assert "subgroup" in str(e)
+
+    # ---- 2. Groth16: GPU proofs verified on the GPU, decisions equal to the gnark-verifier restatement
+    cases = [("bn254", 40, 5, 1, 6, 2, "solidity"), ("bls12_377", 40, 5, 2, 5, 1, "default"), ("bw6_761", 24, 4, 1, 4, 0, "default"),
+             ("bn254", 24, 4, 0, 0, 0, "default")]
+    for cname, ncons, npub, ncommit, npc, npubc, kind in cases:
+        cx = OC.ctx(cname)
+        q = cx.r
+        L = layout.Layout(cname)
+        rnd = random.Random(ncons * 7 + ncommit)
+        cs, W0 = OG.synthetic_circuit(ncons, npub, q, seed=ncons, n_commit=ncommit, n_private_committed=npc,
+                                      n_public_committed=npubc)
+        tox = OG.Toxic(*(rnd.randrange(1, q) for _ in range(5)), sigmas=[rnd.randrange(1, q) for _ in range(ncommit)])
+        opk, ex = OG.setup(cs, cx, tox)
+        ovk = OG.verifying_key(cs, cx, tox, ex)
+        ccs, pk, vk = ccs_from_oracle(cs, L.id), pk_from_oracle(opk, L.id), vk_from_oracle(ovk, L.id)
+        w = T.Witness(L.id, W0[1:cs.nb_public], W0[cs.nb_public:cs.nb_public + ccs.nb_secret])
+        opts = [prover.WithProverTargetSolidityVerifier()] if kind == "solidity" else []
+        try:
+            proof = prover.ProveWithWitness(L.id, ccs, pk, w, *opts)       # un-pinned randomness
+            sol = ccs.solve(w, lambda i, v: proof.Commitments[i], kind)
+            public = sol.values[1:cs.nb_public]
+            assert OG.verify(ovk, proof.points(), public, cx, kind)
+            t0 = time.time()
+            verifier.Verify(proof, vk, public, *opts)
+            out["verify_ms"]["%s/%d" % (cname, ncommit)] = round(1e3 * (time.time() - t0), 1)
+            rejected = 0
+            for idx in (0, -1):         # a public wire may be unused by the circuit: decisions must AGREE with the oracle
+                wrong = list(public)
+                wrong[idx] = (wrong[idx] + 1) % q
+                want = OG.verify(ovk, proof.points(), wrong, cx, kind)
+                assert verifier.verify(proof, vk, wrong, *opts) == want, (cname, ncommit, idx)
+                rejected += not want
+            assert rejected, "no wrong public input was rejected"
+            bad = T.Proof(L.id)
+            bad.Ar, bad.Bs, bad.Commitments, bad.CommitmentPok = proof.Ar, proof.Bs, proof.Commitments, proof.CommitmentPok
+            bad.Krs = L.enc_affine([cx.G1.add(proof.points()["Krs"], cx.g1)], 1)
+            assert not verifier.verify(bad, vk, public, *opts)
+        finally:
+            prover.release_proving_key(pk)
+    out["ok"] = True
+    out["launches"] = int(capi.lib.b200_launch_count())
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -25,3 +25,25 @@ def pk_from_oracle(pk, curve_id):
         infinity_a=np.array(pk["InfinityA"], dtype=np.uint8), infinity_b=np.array(pk["InfinityB"], dtype=np.uint8),
         commitment_keys=[{"Basis": a1(k["Basis"]), "BasisExpSigma": a1(k["BasisExpSigma"])} for k in pk["CommitmentKeys"]],
     )
+
+
+def vk_from_oracle(vk, curve_id):
+    """oracle.groth16.verifying_key(...) -> davinci_node_b200.setup.VerifyingKey"""
+    from davinci_node_b200.setup import VerifyingKey
+    L = Layout(curve_id)
+    a1 = lambda pts: L.enc_affine(pts, 1)
+    a2 = lambda pts: L.enc_affine(pts, 2)
+    return VerifyingKey(curve_id=curve_id, g1_alpha=a1([vk["G1"]["Alpha"]]), g1_K=a1(vk["G1"]["K"]),
+                        g2_beta=a2([vk["G2"]["Beta"]]), g2_gamma=a2([vk["G2"]["Gamma"]]), g2_delta=a2([vk["G2"]["Delta"]]),
+                        commitment_keys=[{"G": a2([k["G"]]), "GSigmaNeg": a2([k["GSigmaNeg"]])} for k in vk["CommitmentKeys"]],
+                        public_and_commitment_committed=[list(w) for w in vk["public_committed"]])
+
+
+def proof_from_oracle(proof, curve_id):
+    """oracle.groth16.prove(...) point dict -> davinci_node_b200.gnark_types.Proof"""
+    L = Layout(curve_id)
+    p = T.Proof(curve_id)
+    p.Ar, p.Krs, p.Bs = L.enc_affine([proof["Ar"]], 1), L.enc_affine([proof["Krs"]], 1), L.enc_affine([proof["Bs"]], 2)
+    p.Commitments = [L.enc_affine([c], 1) for c in proof["Commitments"]]
+    p.CommitmentPok = L.enc_affine([proof.get("CommitmentPok")], 1)
+    return p

@@ -494,6 +494,45 @@ def emit_field(name, p, n):
     return "\n".join(hdr) + "\n"
 
 
+# ----------------------------------------------------------------------------- pairing constants
+def pairing_table():
+    """(curve, p, r, k, m_half, m_0, u0, u1, D-twist): F_{p^k} = Fp[w] / (w^k + m_half w^(k/2) + m_0) and the image
+    u = u0 + u1 w^(k/2) of the Fp2 generator (u1 = 0: G2 lives over Fp).  Towers of gnark-crypto:
+      BN254      u^2 = -1, w^6 = 9 + u   BLS12-381  u^2 = -1, w^6 = 1 + u
+      BLS12-377  u^2 = -5, w^6 = u       BW6-761    k = 6, w^6 = -4"""
+    from oracle import params as PR
+    return [
+        ("bn254", PR.BN254.p, PR.BN254.r, 12, -18, 82, -9, 1, True),
+        ("bls12_377", PR.BLS12_377.p, PR.BLS12_377.r, 12, 0, 5, 0, 1, True),
+        ("bls12_381", PR.BLS12_381.p, PR.BLS12_381.r, 12, -2, 2, -1, 1, False),
+        ("bw6_761", PR.BW6_761.p, PR.BW6_761.r, 6, 0, 4, 0, 0, False),
+    ]
+
+
+def emit_pairing():
+    out = ["// GENERATED by tools/gen_field.py - do not edit.  Extension-field shapes and final exponents (p^k - 1) / r of the",
+           "// reduced Tate pairing (csrc/pairing.cuh).",
+           "#pragma once", "#include <stdint.h>",
+           "#ifdef B200_PAIRING_HOST", "#define B200_PAIRING_CONST static const", "#define B200_PAIRING_FN static inline",
+           "#else", "#define B200_PAIRING_CONST static __device__ const",
+           "#define B200_PAIRING_FN static __device__ __forceinline__", "#endif",
+           "namespace b200 {"]
+    for name, p, r, k, mh, m0, u0, u1, dtw in pairing_table():
+        assert (p ** k - 1) % r == 0
+        e = (p ** k - 1) // r
+        nw = (e.bit_length() + 31) // 32
+        out.append("B200_PAIRING_CONST uint32_t k_final_exp_%s[%d] = {%s};" % (
+            name, nw, ", ".join("0x%08xu" % x for x in limbs(e, nw))))
+        out.append("struct pairing_%s {" % name)
+        out.append("  static constexpr int K = %d, MH = %d, M0 = %d, U0 = %d, U1 = %d;" % (k, mh, m0, u0, u1))
+        out.append("  static constexpr bool DTWIST = %s;" % ("true" if dtw else "false"))
+        out.append("  static constexpr int FE_BITS = %d;" % e.bit_length())
+        out.append("  B200_PAIRING_FN uint32_t final_exp(int i) { return k_final_exp_%s[i]; }" % name)
+        out.append("};")
+    out.append("}  // namespace b200")
+    return "\n".join(out) + "\n"
+
+
 def main():
     out_dir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(
         os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "davinci-node_b200", "csrc", "gen")
@@ -506,6 +545,12 @@ def main():
             with open(path, "w") as fh:
                 fh.write(txt)
         print("generated", path, "(%d limbs)" % n)
+    path = os.path.join(out_dir, "pairing_consts.cuh")
+    txt = emit_pairing()
+    if (open(path).read() if os.path.exists(path) else None) != txt:
+        with open(path, "w") as fh:
+            fh.write(txt)
+    print("generated", path)
 
 
 if __name__ == "__main__":
