@@ -149,3 +149,31 @@ def test_solidity_abi_encoding():
     bad = T.Proof(2)
     with pytest.raises(solidity.SolidityProofError):
         solidity.Groth16CommitmentProof().FromGnarkProof(bad)
+
+
+def test_product_and_build_never_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under davinci-node_b200/ (package, build recipe, CUDA sources) and not the
+    field generator the build runs may import, include or execute it; bench.py may only through its cpu_baseline /
+    reference legs (oracle.cport)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b|#\s*include\s+[\"<].*oracle)", re.M)
+    offenders = []
+    for base, _, files in os.walk(os.path.join(root, "davinci-node_b200")):
+        if os.sep + "build" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".go", ".tmpl")):
+                txt = open(os.path.join(base, f), errors="replace").read()
+                if pat.search(txt) or "oracle/" in txt and "dlopen" in txt:
+                    offenders.append(os.path.join(base, f))
+    gen = open(os.path.join(root, "tools", "gen_field.py")).read()
+    if pat.search(gen):
+        offenders.append("tools/gen_field.py")
+    assert not offenders, offenders
+    # bench.py: oracle imports only inside the CPU-baseline prover (class CpuProver), which the B200 arm's timed region
+    # never touches
+    bench = open(os.path.join(root, "bench.py")).read()
+    lo, hi = bench.index("class CpuProver"), bench.index("def cpu_reference_run")
+    for m in re.finditer(r"^\s*(from\s+oracle\b|import\s+oracle\b)", bench, re.M):
+        assert lo < m.start() < hi, "oracle imported outside CpuProver: " + bench[m.start():m.start() + 60]

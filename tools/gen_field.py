@@ -395,16 +395,27 @@ def prog_from_mont(n, p):
 
 
 # ----------------------------------------------------------------------------- fields
+def curve_moduli():
+    """name -> (p, r) from the product's own table (davinci-node_b200/layout.py; loaded by path: the package itself
+    needs the library this generator is a build step of)."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "davinci-node_b200", "layout.py")
+    spec = importlib.util.spec_from_file_location("_b200_layout", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return {v[0]: (v[1], v[2]) for v in mod.CURVES.values()}
+
+
 def field_table():
-    from oracle import params as PR
+    M = curve_moduli()
     return [
-        ("bn254_fp", PR.BN254.p, 8),
-        ("bn254_fr", PR.BN254.r, 8),
-        ("bls12_377_fp", PR.BLS12_377.p, 12),
-        ("bls12_377_fr", PR.BLS12_377.r, 8),
-        ("bls12_381_fp", PR.BLS12_381.p, 12),
-        ("bls12_381_fr", PR.BLS12_381.r, 8),
-        ("bw6_761_fp", PR.BW6_761.p, 24),
+        ("bn254_fp", M["bn254"][0], 8),
+        ("bn254_fr", M["bn254"][1], 8),
+        ("bls12_377_fp", M["bls12_377"][0], 12),
+        ("bls12_377_fr", M["bls12_377"][1], 8),
+        ("bls12_381_fp", M["bls12_381"][0], 12),
+        ("bls12_381_fr", M["bls12_381"][1], 8),
+        ("bw6_761_fp", M["bw6_761"][0], 24),
         # bw6_761_fr == bls12_377_fp (same modulus): aliased in field.cuh
     ]
 
@@ -500,12 +511,12 @@ def pairing_table():
     u = u0 + u1 w^(k/2) of the Fp2 generator (u1 = 0: G2 lives over Fp).  Towers of gnark-crypto:
       BN254      u^2 = -1, w^6 = 9 + u   BLS12-381  u^2 = -1, w^6 = 1 + u
       BLS12-377  u^2 = -5, w^6 = u       BW6-761    k = 6, w^6 = -4"""
-    from oracle import params as PR
+    M = curve_moduli()
     return [
-        ("bn254", PR.BN254.p, PR.BN254.r, 12, -18, 82, -9, 1, True),
-        ("bls12_377", PR.BLS12_377.p, PR.BLS12_377.r, 12, 0, 5, 0, 1, True),
-        ("bls12_381", PR.BLS12_381.p, PR.BLS12_381.r, 12, -2, 2, -1, 1, False),
-        ("bw6_761", PR.BW6_761.p, PR.BW6_761.r, 6, 0, 4, 0, 0, False),
+        ("bn254",) + M["bn254"] + (12, -18, 82, -9, 1, True),
+        ("bls12_377",) + M["bls12_377"] + (12, 0, 5, 0, 1, True),
+        ("bls12_381",) + M["bls12_381"] + (12, -2, 2, -1, 1, False),
+        ("bw6_761",) + M["bw6_761"] + (6, 0, 4, 0, 0, False),
     ]
 
 
