@@ -516,7 +516,10 @@ __global__ void k_pairing_miller(const typename Cfg::Fp::El* g1, const typename 
   const uint32_t i = blockIdx.x;
   if (threadIdx.x != 0 || i >= n) return;
   typename PT::Ext f;
-  const bool in_subgroup = PT::miller(f, g1 + 2 * (size_t)i, g2 + 2 * PT::NQ * (size_t)i);
+  typename Cfg::Fp::El P[2], Q[2 * PT::NQ];      // operands in local memory: miller() takes plain pointers
+  for (int j = 0; j < 2; j++) P[j] = g1[2 * (size_t)i + j];
+  for (int j = 0; j < 2 * PT::NQ; j++) Q[j] = g2[2 * PT::NQ * (size_t)i + j];
+  const bool in_subgroup = PT::miller(f, P, Q);
   f_out[i] = f;
   flags[i] = in_subgroup ? 0u : 1u;
 }
