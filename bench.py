@@ -188,6 +188,36 @@ class CpuProver:
         return dt
 
 
+def cpu_blob_commit_baseline(reps=20):
+    """CPU leg of the blob config: the 4096-point BLS12-381 G1 MSM a commitment is (types/blobs.go:90 ->
+    gokzg4844 BlobToKZGCommitment), timed through oracle/c's Pippenger on every host thread, valid subgroup points,
+    uniform 255-bit scalars.  kind "port" (go-eth-kzg cannot be built here)."""
+    import numpy as np
+    from oracle import cport
+    from oracle import curve as OC
+    lib, T = cport.lib(), cport.host_threads()
+    p_ = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    r_ = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    fp_l, fr_l = 6, 4
+    cx = OC.ctx("bls12_381")
+    base = BW.enc_mont([cx.g1[0], cx.g1[1]], p_, fp_l)
+    pts = np.zeros((4096, 2 * fp_l), dtype=np.uint64)
+    assert lib.oc_gen_points(3, 1, cport.p(base), 7000003, 4096, cport.p(pts), T) == 0
+    rng = np.random.default_rng(9)
+    canon = BW.rand_canonical(rng, 4096, fr_l, r_.bit_length())
+    sc = np.empty_like(canon)
+    assert lib.oc_fr_to_mont(3, cport.p(canon), cport.p(sc), 4096, T) == 0
+    out = np.zeros(2 * fp_l, dtype=np.uint64)
+    assert lib.oc_msm(3, 1, cport.p(pts), cport.p(sc), 4096, None, cport.p(out), T) == 0
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        assert lib.oc_msm(3, 1, cport.p(pts), cport.p(sc), 4096, None, cport.p(out), T) == 0
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": 1.0 / dt, "unit": "commitments/s", "cores": T, "kind": "port",
+            "sample": "%d x the 4096-point BLS12-381 G1 MSM of one commitment (%.2f ms each) on %d threads; the blob -> "
+                      "scalar decoding (4096 reductions) is not included" % (reps, dt * 1e3, T)}
+
+
 def cpu_reference_run(cfg_name, logn, mix, steps, warmup, nparts=10, full_proof=True):
     """Times the CPU arm.  Warm-up step 0 is ONE FULL proof of the workload (when full_proof); every other step is a
     bounded sample: component i mod 10 of a full-size proof (oracle/c/oracle.cpp prove_impl), which runs exactly the code
@@ -811,6 +841,8 @@ def blob_arm(args, rank, local_rank, world):
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 131072 * batch, "d2h_bytes_per_step": 48 * batch},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "blob_eval_data_flow_ms": flow_ms, "cpu_baseline": None}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_blob_commit_baseline()
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
