@@ -6,7 +6,8 @@ The reference verifies every proof right after proving it (/root/reference/circu
 
   host (this file)   commitment challenges = hash-to-field over (commitment || public committed inputs), the fold
                      challenge of several commitments, the bookkeeping of which points are paired;
-  GPU  (C ABI)       the public-input MSM  L = sum_i pub_i K_i + sum_j chal_j K_(np+j) + sum_j C_j   (b200_msm),
+  GPU  (C ABI)       the subgroup check of Bs ((r - 1) Bs == -Bs, b200_msm on G2; Ar / Krs are checked by the Miller loop),
+                     the public-input MSM  L = sum_i pub_i K_i + sum_j chal_j K_(np+j) + sum_j C_j   (b200_msm),
                      the folded commitment sum_j fold^j C_j (b200_msm), and the two product-of-pairings checks
                          e(C_fold, GSigmaNeg) e(PoK, G) == 1
                          e(-Ar, Bs) e(alpha, beta) e(L, gamma) e(Krs, delta) == 1            (b200_pairing_check).
@@ -34,12 +35,31 @@ def _neg_g1(L: Layout, buf):
     return L.enc_affine([None if pt is None else (pt[0], (-pt[1]) % L.p)], 1)
 
 
-def _msm_g1(L: Layout, point_bufs, scalars, device):
+def _msm(L: Layout, group, point_bufs, scalars, device):
     pts = np.concatenate([np.asarray(b, dtype=np.uint8) for b in point_bufs])
     sc = L.enc_fr(scalars)
-    out = np.zeros(L.affine_bytes(1), dtype=np.uint8)
-    capi.check(capi.lib.b200_msm(L.id, 1, pts.ctypes.data, sc.ctypes.data, len(scalars), out.ctypes.data, device))
+    out = np.zeros(L.affine_bytes(group), dtype=np.uint8)
+    capi.check(capi.lib.b200_msm(L.id, group, pts.ctypes.data, sc.ctypes.data, len(scalars), out.ctypes.data, device))
     return out
+
+
+def _msm_g1(L: Layout, point_bufs, scalars, device):
+    return _msm(L, 1, point_bufs, scalars, device)
+
+
+def _neg_g2(L: Layout, buf):
+    pt = L.dec_affine(buf, 2)[0]
+    if pt is None:
+        return L.enc_affine([None], 2)
+    y = pt[1]
+    ny = (-y) % L.p if L.coord_width(2) == 1 else ((-y[0]) % L.p, (-y[1]) % L.p)
+    return L.enc_affine([(pt[0], ny)], 2)
+
+
+def _g2_in_subgroup(L: Layout, buf, device):
+    """r * Q == infinity, checked as (r - 1) * Q == -Q with the G2 MSM (gnark: G2Affine.IsInSubGroup)."""
+    got = _msm(L, 2, [buf], [L.r - 1], device)
+    return bytes(got) == bytes(_neg_g2(L, buf))
 
 
 def pairing_check(curve_id, g1_bufs, g2_bufs, device=-1, want_gt=False):
@@ -96,8 +116,17 @@ def Verify(proof, vk: VerifyingKey, public_witness, *opts, device=-1):
             raise VerificationError("commitment proof of knowledge: pairing check failed")
     kbufs = [vk.g1_K[i * ab1:(i + 1) * ab1] for i in range(nK)]
     Lpt = _msm_g1(L, kbufs + list(proof.Commitments), pub + chals + [1] * ncm, device)
-    ok = pairing_check(L.id, [_neg_g1(L, proof.Ar), vk.g1_alpha, Lpt, proof.Krs],
-                       [proof.Bs, vk.g2_beta, vk.g2_gamma, vk.g2_delta], device)
+    # proof.isValid(): Ar, Krs, Bs in the order-r subgroups.  The Miller loop over r reports the G1 points (r * P must
+    # end at infinity); Bs needs its own check
+    if not _g2_in_subgroup(L, proof.Bs, device):
+        raise VerificationError("proof is invalid: points not in the correct subgroup")
+    try:
+        ok = pairing_check(L.id, [_neg_g1(L, proof.Ar), vk.g1_alpha, Lpt, proof.Krs],
+                           [proof.Bs, vk.g2_beta, vk.g2_gamma, vk.g2_delta], device)
+    except capi.B200Error as e:
+        if "subgroup" in str(e):
+            raise VerificationError("proof is invalid: points not in the correct subgroup") from e
+        raise
     if not ok:
         raise VerificationError("pairing doesn't match")
 

@@ -91,6 +91,14 @@ def main():
             bad.Ar, bad.Bs, bad.Commitments, bad.CommitmentPok = proof.Ar, proof.Bs, proof.Commitments, proof.CommitmentPok
             bad.Krs = L.enc_affine([cx.G1.add(proof.points()["Krs"], cx.g1)], 1)
             assert not verifier.verify(bad, vk, public, *opts)
+            # Bs on the twist but outside the order-r subgroup (gnark: proof.isValid())
+            from test_verifier_cpu import _twist_point_outside_subgroup
+            bad.Krs, bad.Bs = proof.Krs, L.enc_affine([_twist_point_outside_subgroup(cx)], 2)
+            try:
+                verifier.Verify(bad, vk, public, *opts)
+                raise AssertionError("a Bs outside the subgroup was accepted")
+            except verifier.VerificationError as e:
+                assert "subgroup" in str(e)
         finally:
             prover.release_proving_key(pk)
     out["ok"] = True

@@ -14,17 +14,29 @@ from oracle import hashes as H
 from oracle import pairing
 
 
+def _twist_point_outside_subgroup(cx):
+    G2 = cx.G2
+    rnd = random.Random(17)
+    while True:
+        x = (rnd.randrange(cx.p), rnd.randrange(cx.p)) if isinstance(cx.g2[0], tuple) else rnd.randrange(cx.p)
+        F = G2.F
+        y = F.sqrt(F.add(F.mul(F.sqr(x), x), G2.b))
+        if y is not None and G2.on_curve((x, y)) and G2.mul((x, y), cx.r) is not None:
+            return (x, y)
+
+
 @pytest.fixture
 def fake_gpu(monkeypatch):
     from davinci_node_b200 import capi, verifier
     from davinci_node_b200.layout import Layout
     calls = {"msm": 0, "pairing": 0}
 
-    def msm(L, point_bufs, scalars, device):
+    def msm(L, group, point_bufs, scalars, device):
         cx = OC.ctx(L.name)
-        pts = [L.dec_affine(b, 1)[0] for b in point_bufs]
+        G = cx.G1 if group == 1 else cx.G2
+        pts = [L.dec_affine(b, group)[0] for b in point_bufs]
         calls["msm"] += 1
-        return L.enc_affine([cx.G1.msm_naive(pts, [int(s) % L.r for s in scalars])], 1)
+        return L.enc_affine([G.msm_naive(pts, [int(s) % L.r for s in scalars])], group)
 
     def check(curve_id, g1_bufs, g2_bufs, device=-1, want_gt=False):
         L = Layout(curve_id)
@@ -33,7 +45,7 @@ def fake_gpu(monkeypatch):
         assert len(g1_bufs) == len(g2_bufs)
         return pr.product_is_one([(L.dec_affine(a, 1)[0], L.dec_affine(b, 2)[0]) for a, b in zip(g1_bufs, g2_bufs)])
 
-    monkeypatch.setattr(verifier, "_msm_g1", msm)
+    monkeypatch.setattr(verifier, "_msm", msm)
     monkeypatch.setattr(verifier, "pairing_check", check)
     monkeypatch.setattr(capi, "init_once", lambda: None)
     return calls
@@ -90,6 +102,11 @@ def test_verify_mirror_agrees_with_gnark_verifier_restatement(fake_gpu, cname, k
         short.Commitments = short.Commitments[:-1]
         with pytest.raises(verifier.VerificationError, match="number of commitments"):
             verifier.Verify(short, vk, public, *opts)
+    # Bs on the twist but outside the order-r subgroup (gnark: proof.isValid())
+    rogue = proof_from_oracle(oproof, L.id)
+    rogue.Bs = L.enc_affine([_twist_point_outside_subgroup(cx)], 2)
+    with pytest.raises(verifier.VerificationError, match="subgroup"):
+        verifier.Verify(rogue, vk, public, *opts)
     with pytest.raises(verifier.VerificationError, match="invalid witness size"):
         verifier.Verify(proof, vk, public[:-1], *opts)
     other_curve = proof_from_oracle(oproof, L.id)
