@@ -29,6 +29,10 @@ import (
 	"unsafe"
 
 	"github.com/consensys/gnark-crypto/ecc"
+	fr_bls12377 "github.com/consensys/gnark-crypto/ecc/bls12-377/fr"
+	fr_bls12381 "github.com/consensys/gnark-crypto/ecc/bls12-381/fr"
+	fr_bn254 "github.com/consensys/gnark-crypto/ecc/bn254/fr"
+	fr_bw6761 "github.com/consensys/gnark-crypto/ecc/bw6-761/fr"
 	"github.com/consensys/gnark/backend"
 	"github.com/consensys/gnark/backend/groth16"
 	groth16_bls12377 "github.com/consensys/gnark/backend/groth16/bls12-377"
@@ -192,5 +196,42 @@ func GPUProverWithWitness(curveID ecc.ID, ccs constraint.ConstraintSystem, pk gr
 
 	default:
 		return nil, fmt.Errorf("B200 proving not supported for curve %s", curveID)
+	}
+}
+
+// VerifyB200 is groth16.Verify (circuits/artifacts.go:604-613) with its MultiExp and pairing checks on the GPU.  Same
+// arguments, same error cases; opt-in - the reference's own groth16.Verify call keeps working unchanged.
+func VerifyB200(proof groth16.Proof, vk groth16.VerifyingKey, publicWitness witness.Witness, opts ...backend.VerifierOption) error {
+	switch p := proof.(type) {
+	case *groth16_bn254.Proof:
+		k, ok := vk.(*groth16_bn254.VerifyingKey)
+		w, ok2 := publicWitness.Vector().(fr_bn254.Vector)
+		if !ok || !ok2 {
+			return fmt.Errorf("verifying key / witness type mismatch for BN254: got %T, %T", vk, publicWitness.Vector())
+		}
+		return verifyBN254(p, k, w, opts...)
+	case *groth16_bls12377.Proof:
+		k, ok := vk.(*groth16_bls12377.VerifyingKey)
+		w, ok2 := publicWitness.Vector().(fr_bls12377.Vector)
+		if !ok || !ok2 {
+			return fmt.Errorf("verifying key / witness type mismatch for BLS12_377: got %T, %T", vk, publicWitness.Vector())
+		}
+		return verifyBLS12377(p, k, w, opts...)
+	case *groth16_bls12381.Proof:
+		k, ok := vk.(*groth16_bls12381.VerifyingKey)
+		w, ok2 := publicWitness.Vector().(fr_bls12381.Vector)
+		if !ok || !ok2 {
+			return fmt.Errorf("verifying key / witness type mismatch for BLS12_381: got %T, %T", vk, publicWitness.Vector())
+		}
+		return verifyBLS12381(p, k, w, opts...)
+	case *groth16_bw6761.Proof:
+		k, ok := vk.(*groth16_bw6761.VerifyingKey)
+		w, ok2 := publicWitness.Vector().(fr_bw6761.Vector)
+		if !ok || !ok2 {
+			return fmt.Errorf("verifying key / witness type mismatch for BW6_761: got %T, %T", vk, publicWitness.Vector())
+		}
+		return verifyBW6761(p, k, w, opts...)
+	default:
+		return fmt.Errorf("B200 verification not supported for proof type %T", proof)
 	}
 }
