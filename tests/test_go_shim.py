@@ -142,3 +142,66 @@ def test_exported_surface_matches_the_reference_package():
                 "func (b *Blob) ComputeProof(point *big.Int) (proof KZGProof, claim *big.Int, err error)"):
         assert sig in blobs, sig
     assert blobs.count("{") == blobs.count("}") and blobs.count("(") == blobs.count(")")
+
+
+def _strip_go(text):
+    """Go source with comments, string / rune literals and raw strings blanked out (positions preserved)."""
+    out, i, n = [], 0, len(text)
+    while i < n:
+        c = text[i]
+        if text.startswith("//", i):
+            j = text.find("\n", i)
+            j = n if j < 0 else j
+            out.append(" " * (j - i))
+            i = j
+        elif text.startswith("/*", i):
+            j = text.find("*/", i + 2)
+            j = n if j < 0 else j + 2
+            out.append("".join(ch if ch == "\n" else " " for ch in text[i:j]))
+            i = j
+        elif c in "\"'`":
+            j = i + 1
+            while j < n and text[j] != c:
+                j += 2 if (text[j] == "\\" and c != "`") else 1
+            out.append(c + " " * (j - i - 1) + c)
+            i = j + 1
+        else:
+            out.append(c)
+            i += 1
+    return "".join(out)
+
+
+def test_go_files_are_lexically_balanced_and_declare_what_they_use():
+    """No Go toolchain here: at least every bracket closes, every import alias is used, and every function the
+    dispatcher calls (prove<ID> / verify<ID>) is defined by a generated file."""
+    import glob
+    import re
+    gofiles = sorted(glob.glob(os.path.join(GO, "prover", "*.go")) + glob.glob(os.path.join(GO, "types", "*.go")))
+    assert gofiles
+    defined, called = set(), set()
+    for path in gofiles:
+        src = _strip_go(open(path).read())
+        stack = []
+        pairs = {")": "(", "]": "[", "}": "{"}
+        for pos, ch in enumerate(src):
+            if ch in "([{":
+                stack.append((ch, pos))
+            elif ch in ")]}":
+                assert stack and stack[-1][0] == pairs[ch], "%s: unbalanced %r at offset %d" % (os.path.basename(path), ch, pos)
+                stack.pop()
+        assert not stack, "%s: unclosed %r" % (os.path.basename(path), stack[-1])
+        # import aliases / package names must be referenced
+        m = re.search(r"\bimport\s*\(\s*(.*?)\)", open(path).read().split('import "C"')[-1], re.S)
+        if m:
+            for line in m.group(1).splitlines():
+                line = line.strip()
+                if not line or line.startswith("//"):
+                    continue
+                parts = line.split()
+                pkg = parts[-1].strip('"')
+                alias = parts[0] if len(parts) == 2 else pkg.split("/")[-1]
+                body = src[src.index(m.group(1)[:20]) + len(m.group(1)):] if m.group(1)[:20] in src else src
+                assert re.search(r"\b%s\." % re.escape(alias), body), "%s: import %s (%s) unused" % (os.path.basename(path), alias, pkg)
+        defined |= set(re.findall(r"^func\s+(\w+)\s*\(", src, re.M))
+        called |= set(re.findall(r"\b((?:prove|verify|register)(?:BN254|BLS12377|BLS12381|BW6761))\s*\(", src))
+    assert called and called <= defined, called - defined
