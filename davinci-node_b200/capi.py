@@ -71,6 +71,7 @@ _PROTOS = {
     "b200_points_compress_dev": (_i, [_i, _i, _vp, _u64, _vp, _vp]),
     "b200_gt_bytes": (_u64, [_i]),
     "b200_pairing_check": (_i, [_i, _vp, _vp, _u32, C.POINTER(_i), _vp, _i]),
+    "b200_pairing_check_batch": (_i, [_i, _vp, _vp, _u32, _u32, _vp, _i]),
     "b200_fixed_base_dev": (_i, [_i, _i, _vp, _vp, _u64, _vp, _vp]),
     "b200_bases_create_dev": (_i, [_i, _i, _vp, _u64, _i, C.POINTER(_u64), _vp]),
     "b200_bases_release": (_i, [_u64]),

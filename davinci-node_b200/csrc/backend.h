@@ -225,6 +225,10 @@ struct CurveBackend {
   virtual size_t gt_bytes() const = 0;
   virtual void pairing_check(const void* d_g1, const void* d_g2, uint32_t n, void* d_f, void* d_gt, uint32_t* d_flags,
                              cudaStream_t s) = 0;
+  // n_checks independent checks of `per` pairs each, one thread per pair / per check; d_results[c] = 1 holds, 0 does not,
+  // -1 some G1 point of check c is outside the subgroup.  d_f: per * n_checks * gt_bytes(), d_flags: per * n_checks
+  virtual void pairing_check_batch(const void* d_g1, const void* d_g2, uint32_t per, uint32_t n_checks, void* d_f,
+                                   uint32_t* d_flags, int32_t* d_results, cudaStream_t s) = 0;
   virtual void blob_to_scalars(const void* d_blob, void* d_scalars, uint32_t n, uint32_t* d_err, cudaStream_t s) = 0;
   // KZG opening (EIP-4844 compute_kzg_proof_impl): roots = w^brp(i) table; kzg_open turns the blob's scalars p and
   // the point z (32 big-endian bytes on the device) into the quotient evaluations q and y = p(z) (32 bytes).

@@ -550,6 +550,30 @@ int b200_pairing_check(int curve_id, const void* g1, const void* g2, uint32_t n,
   });
 }
 
+int b200_pairing_check_batch(int curve_id, const void* g1, const void* g2, uint32_t per, uint32_t n_checks,
+                             int32_t* results_out, int device) {
+  return guarded([&] {
+    CurveBackend& cb = curve(curve_id);
+    if (n_checks && !results_out) throw std::runtime_error("results_out is null");
+    const uint64_t n = (uint64_t)per * n_checks;
+    if (n && (!g1 || !g2)) throw std::runtime_error("null input with pairs > 0");
+    if (per > 64 || n > (1u << 20)) throw std::runtime_error("pairing check batch: at most 64 pairs per check and 2^20 pairs");
+    if (!n_checks) return;
+    DeviceGuard dg(device);
+    ScopedStream st;
+    const size_t b1 = cb.affine_bytes(1), b2 = cb.affine_bytes(2), gb = cb.gt_bytes();
+    ScopedDev d1(n * b1), d2(n * b2), df(n * gb), dfl(n * sizeof(uint32_t)), dres(n_checks * sizeof(int32_t));
+    if (n) {
+      B200_CUDA(cudaMemcpyAsync(d1.p, g1, n * b1, cudaMemcpyHostToDevice, st.s));
+      B200_CUDA(cudaMemcpyAsync(d2.p, g2, n * b2, cudaMemcpyHostToDevice, st.s));
+      B200_CUDA(cudaMemsetAsync(dfl.p, 0, n * sizeof(uint32_t), st.s));
+    }
+    cb.pairing_check_batch(d1.p, d2.p, per, n_checks, df.p, (uint32_t*)dfl.p, (int32_t*)dres.p, st.s);
+    B200_CUDA(cudaMemcpyAsync(results_out, dres.p, n_checks * sizeof(int32_t), cudaMemcpyDeviceToHost, st.s));
+    B200_CUDA(cudaStreamSynchronize(st.s));
+  });
+}
+
 // ---------------------------------------------------------------------------------- key artefacts
 uint64_t b200_compressed_bytes(int c, int g) { return backend_by_id(c) && (g == 1 || g == 2) ? backend_by_id(c)->compressed_bytes(g) : 0; }
 

@@ -523,6 +523,44 @@ __global__ void k_pairing_miller(const typename Cfg::Fp::El* g1, const typename 
   f_out[i] = f;
   flags[i] = in_subgroup ? 0u : 1u;
 }
+// Batch variants: thread t handles pair t / check t, so the lanes of a warp run INDEPENDENT pairings through one
+// instruction stream (the Miller loop follows the bits of r, the exponentiation the bits of (p^k - 1) / r: no
+// data-dependent control flow once the inversions are Fermat exponentiations).  This is the throughput form of the
+// verifier: checks per second scale with the number of resident threads, not with the latency of one thread.
+template <class Cfg>
+using PairOfBatch = PairingT<typename Cfg::Fp, typename Cfg::Tower, typename Cfg::Fr::Params, true>;
+
+template <class Cfg>
+__global__ void k_pairing_miller_batch(const typename Cfg::Fp::El* g1, const typename Cfg::Fp::El* g2, uint32_t n,
+                                       typename PairOfBatch<Cfg>::Ext* f_out, uint32_t* flags) {
+  using PT = PairOfBatch<Cfg>;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename PT::Ext f;
+  typename Cfg::Fp::El P[2], Q[2 * PT::NQ];
+  for (int j = 0; j < 2; j++) P[j] = g1[2 * (size_t)i + j];
+  for (int j = 0; j < 2 * PT::NQ; j++) Q[j] = g2[2 * PT::NQ * (size_t)i + j];
+  const bool in_subgroup = PT::miller(f, P, Q);
+  f_out[i] = f;
+  flags[i] = in_subgroup ? 0u : 1u;
+}
+template <class Cfg>
+__global__ void k_pairing_finish_batch(const typename PairOfBatch<Cfg>::Ext* f, const uint32_t* flags, uint32_t per,
+                                       uint32_t n_checks, int32_t* results) {
+  using PT = PairOfBatch<Cfg>;
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_checks) return;
+  typename PT::Ext acc, g;
+  PT::ext_one(acc);
+  uint32_t bad = 0;
+  for (uint32_t j = 0; j < per; j++) {
+    g = f[(size_t)c * per + j];
+    bad |= flags[(size_t)c * per + j];
+    PT::ext_mul(acc, acc, g);
+  }
+  PT::final_exp(g, acc);
+  results[c] = bad ? -1 : (PT::ext_is_one(g) ? 1 : 0);
+}
 // One thread: product of the Miller values, final exponentiation, comparison with one.
 template <class Cfg>
 __global__ void k_pairing_finish(const typename PairOf<Cfg>::Ext* f, uint32_t n, typename PairOf<Cfg>::Ext* gt_out,
@@ -890,6 +928,21 @@ struct CurveImpl : CurveBackend {
       B200_CUDA(cudaGetLastError());
     }
     k_pairing_finish<Cfg><<<1, 1, 0, s>>>((const Ext*)d_f, n, (Ext*)d_gt, d_flags + n);
+    prof_count_launches(n ? 2 : 1);
+    B200_CUDA(cudaGetLastError());
+  }
+
+  void pairing_check_batch(const void* d_g1, const void* d_g2, uint32_t per, uint32_t n_checks, void* d_f, uint32_t* d_flags,
+                           int32_t* d_results, cudaStream_t s) override {
+    using Ext = typename PairOfBatch<Cfg>::Ext;
+    const uint32_t n = per * n_checks;
+    if (!n_checks) return;
+    if (n) {
+      k_pairing_miller_batch<Cfg><<<(n + 31) / 32, 32, 0, s>>>((const typename Fp::El*)d_g1, (const typename Fp::El*)d_g2, n,
+                                                               (Ext*)d_f, d_flags);
+      B200_CUDA(cudaGetLastError());
+    }
+    k_pairing_finish_batch<Cfg><<<(n_checks + 31) / 32, 32, 0, s>>>((const Ext*)d_f, d_flags, per, n_checks, d_results);
     prof_count_launches(n ? 2 : 1);
     B200_CUDA(cudaGetLastError());
   }

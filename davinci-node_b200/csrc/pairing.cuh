@@ -15,7 +15,7 @@
 // field products).  gnark's optimal-ate values differ from these by a fixed exponent; the product checks agree.
 //
 // The code is written against the "field concept" of field.cuh (El, add, sub, mul, neg, mul_small, is_zero, eq,
-// set_zero, set_one, inv_bin) and is compiled twice: for the device inside curve_impl.cuh, and - with B200_PQ = __host__
+// set_zero, set_one, inv_bin, inv) and is compiled twice: for the device inside curve_impl.cuh, and - with B200_PQ = __host__
 // and a portable Montgomery field - by tests/host_pairing.cu, where every function below is checked bit for bit against
 // the big-integer pairing of the test oracle on the CPU.
 #pragma once
@@ -30,8 +30,9 @@
 namespace b200 {
 
 // F: prime field of the coordinates; T: extension shape (gen/pairing_consts.cuh); RP: parameter struct of the scalar
-// field (its modulus r drives the Miller loop)
-template <class F, class T, class RP>
+// field (its modulus r drives the Miller loop); FERMAT: invert by a^(p-2) (fixed instruction stream: the choice when the
+// lanes of a warp run independent pairings) instead of the binary GCD (data-dependent loops: fastest for one thread)
+template <class F, class T, class RP, bool FERMAT = false>
 struct PairingT {
   using El = typename F::El;
   static constexpr int K = T::K;
@@ -41,6 +42,13 @@ struct PairingT {
     El c[K];
   };
 
+  static B200_PQ void inv(El& r, const El& a) {
+    if (FERMAT) {
+      F::inv(r, a);
+    } else {
+      F::inv_bin(r, a);
+    }
+  }
   static B200_PQ void ext_zero(Ext& r) {
     for (int i = 0; i < K; i++) F::set_zero(r.c[i]);
   }
@@ -126,7 +134,7 @@ struct PairingT {
       El one, m0, im0;
       F::set_one(one);
       scale_small(m0, one, T::M0);
-      F::inv_bin(im0, m0);
+      inv(im0, m0);
       F::neg(w1.c[K - 1], im0);
       if (T::MH != 0) {
         scale_small(m0, im0, T::MH);
@@ -161,7 +169,7 @@ struct PairingT {
     F::mul(num, tx, tx);
     F::mul_small(num, num, 3);
     F::add(den, ty, ty);
-    F::inv_bin(den, den);
+    inv(den, den);
     F::mul(lam, num, den);
     Ext l;
     line(l, xq, yq, lam, tx, ty);
@@ -179,7 +187,7 @@ struct PairingT {
     El lam, num, den, nx, t;
     F::sub(num, ty, yp);
     F::sub(den, tx, xp);
-    F::inv_bin(den, den);
+    inv(den, den);
     F::mul(lam, num, den);
     Ext l;
     line(l, xq, yq, lam, tx, ty);

@@ -83,6 +83,28 @@ def pairing_check(curve_id, g1_bufs, g2_bufs, device=-1, want_gt=False):
     return (ok, tuple(L.dec_fp(gt))) if want_gt else ok
 
 
+def pairing_check_batch(curve_id, g1_bufs, g2_bufs, pairs_per_check, device=-1):
+    """n independent product checks in one call (b200_pairing_check_batch: one GPU thread per pair and per check).
+    g1_bufs / g2_bufs: flat lists of len n * pairs_per_check point buffers, check c owning the slice
+    [c * pairs_per_check, (c + 1) * pairs_per_check).  Returns a list of True / False / None (None: a G1 point of that
+    check lies outside the order-r subgroup)."""
+    L = Layout(curve_id)
+    per = int(pairs_per_check)
+    if per <= 0 or len(g1_bufs) != len(g2_bufs) or len(g1_bufs) % per:
+        raise ValueError("pairing_check_batch: %d / %d points for checks of %d pairs" % (len(g1_bufs), len(g2_bufs), per))
+    n_checks = len(g1_bufs) // per
+    if not n_checks:
+        return []
+    capi.init_once()
+    g1 = np.concatenate([np.asarray(b, dtype=np.uint8) for b in g1_bufs])
+    g2 = np.concatenate([np.asarray(b, dtype=np.uint8) for b in g2_bufs])
+    if g1.size != len(g1_bufs) * L.affine_bytes(1) or g2.size != len(g2_bufs) * L.affine_bytes(2):
+        raise ValueError("pairing_check_batch: point buffers of the wrong size")
+    res = np.zeros(n_checks, dtype=np.int32)
+    capi.check(capi.lib.b200_pairing_check_batch(L.id, g1.ctypes.data, g2.ctypes.data, per, n_checks, res.ctypes.data, device))
+    return [None if r < 0 else bool(r) for r in res]
+
+
 def Verify(proof, vk: VerifyingKey, public_witness, *opts, device=-1):
     """groth16.Verify: returns None when the proof verifies, raises VerificationError otherwise."""
     L = Layout(vk.curve_id)

@@ -241,6 +241,12 @@ B200_API int b200_points_compress_dev(int curve, int group, const void* d_affine
 B200_API uint64_t b200_gt_bytes(int curve);
 B200_API int b200_pairing_check(int curve, const void* g1_affine, const void* g2_affine, uint32_t n, int* result_out,
                                 void* gt_out, int device);
+/* Throughput form: n_checks independent checks of pairs_per_check pairs each (check c uses pairs [c * per, (c + 1) * per)),
+ * one GPU thread per pair and per check - batches of proofs (sequencer/aggregate.go:503-519 re-verifies every inner proof
+ * of a batch; api/workers.go:353 every worker submission).  results_out[c] = 1 holds, 0 does not, -1 some G1 point of
+ * the check is outside the order-r subgroup. */
+B200_API int b200_pairing_check_batch(int curve, const void* g1_affine, const void* g2_affine, uint32_t pairs_per_check,
+                                      uint32_t n_checks, int32_t* results_out, int device);
 
 /* ---- setup building block / instrumentation -----------------------------------------------------
  * out[i] = [k_i] base as affine points: the fixed-base batch scalar multiplication groth16.Setup is

@@ -135,6 +135,7 @@ struct HostFp {
     }
     r = acc;
   }
+  static void inv(El& r, const El& a) { inv_bin(r, a); }
   static void to_mont(El& r, const uint32_t* canon) {
     El a, r2;
     for (int i = 0; i < N; i++) {
@@ -152,10 +153,10 @@ struct HostFp {
   }
 };
 
-template <class FP, class T, class RP>
+template <class FP, class T, class RP, bool FERMAT = false>
 struct Harness {
   using F = HostFp<FP>;
-  using PT = b200::PairingT<F, T, RP>;
+  using PT = b200::PairingT<F, T, RP, FERMAT>;
   using El = typename F::El;
   static constexpr int N = FP::N;
   static void load(El* dst, const uint32_t* src, int count) {
@@ -209,6 +210,7 @@ using H_bn254 = Harness<b200::bn254_fp, b200::pairing_bn254, b200::bn254_fr>;
 using H_bls12_377 = Harness<b200::bls12_377_fp, b200::pairing_bls12_377, b200::bls12_377_fr>;
 using H_bls12_381 = Harness<b200::bls12_381_fp, b200::pairing_bls12_381, b200::bls12_381_fr>;
 using H_bw6_761 = Harness<b200::bw6_761_fp, b200::pairing_bw6_761, b200::bw6_761_fr>;
+using HF_bn254 = Harness<b200::bn254_fp, b200::pairing_bn254, b200::bn254_fr, true>;   // the batch kernels' variant
 
 }  // namespace
 
@@ -218,6 +220,7 @@ using H_bw6_761 = Harness<b200::bw6_761_fp, b200::pairing_bw6_761, b200::bw6_761
     case 2: { using HH = H_bls12_377; return expr; }  \
     case 3: { using HH = H_bls12_381; return expr; }  \
     case 4: { using HH = H_bw6_761; return expr; }    \
+    case 101: { using HH = HF_bn254; return expr; }   \
     default: return -100;                  \
   }
 

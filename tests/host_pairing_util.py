@@ -8,8 +8,8 @@ ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "host_pairing.cu")
 OUT = os.path.join(HERE, "_build", "libhost_pairing.so")
 CSRC = os.path.join(ROOT, "davinci-node_b200", "csrc")
-CURVE_ID = {"bn254": 1, "bls12_377": 2, "bls12_381": 3, "bw6_761": 4}
-FP_LIMBS = {"bn254": 8, "bls12_377": 12, "bls12_381": 12, "bw6_761": 24}
+CURVE_ID = {"bn254": 1, "bls12_377": 2, "bls12_381": 3, "bw6_761": 4, "bn254_fermat": 101}
+FP_LIMBS = {"bn254": 8, "bls12_377": 12, "bls12_381": 12, "bw6_761": 24, "bn254_fermat": 8}
 _lib = None
 
 
@@ -64,6 +64,7 @@ def g1_coords(P):
 def g2_coords(Q, name):
     if name == "bw6_761":
         return [0, 0] if Q is None else [Q[0], Q[1]]
+    name = name.replace("_fermat", "")
     return [0, 0, 0, 0] if Q is None else [Q[0][0], Q[0][1], Q[1][0], Q[1][1]]
 
 

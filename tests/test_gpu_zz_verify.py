@@ -25,3 +25,14 @@ def test_gpu_pairing_and_groth16_verify():
     res = json.loads(line)
     assert res["ok"]
     print("pairing / verify wall ms:", res["pairing_ms"], res["verify_ms"])
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="batch pairing kernels not yet run on hardware (GPU budget exhausted); CPU-verified template")
+def test_gpu_pairing_check_batch():
+    r = subprocess.run([sys.executable, os.path.join(HERE, "gpu_verify_worker.py"), "--batch"], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["ok"]
+    print("batched pairing checks per second:", res["checks_per_s"])

@@ -65,3 +65,16 @@ def test_product_check_and_edge_cases(name):
             if y is not None and cx.G1.on_curve((x, y)) and cx.G1.mul((x, y), cx.r) is not None:
                 break
         assert HP.check(name, [((x, y), Q)]) == -1
+
+
+def test_fermat_inversion_variant_is_the_same_function():
+    """PairingT<..., FERMAT = true> (what the batch kernels instantiate: a^(p-2) instead of the binary GCD) gives the
+    same Miller values and decisions."""
+    pr = pairing.get("bn254")
+    cx = pr.cx
+    P, Q = cx.G1.mul(cx.g1, 77), cx.G2.mul(cx.g2, 1234567)
+    f, in_sub = HP.pair("bn254_fermat", P, Q, which=0)
+    assert in_sub and f == pr.miller(P, Q)
+    a = 991
+    assert HP.check("bn254_fermat", [(cx.G1.mul(cx.g1, a), cx.g2), (cx.G1.neg(cx.g1), cx.G2.mul(cx.g2, a))]) == 1
+    assert HP.check("bn254_fermat", [(cx.G1.mul(cx.g1, a), cx.g2), (cx.G1.neg(cx.g1), cx.G2.mul(cx.g2, a + 1))]) == 0
