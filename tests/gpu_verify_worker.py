@@ -106,10 +106,20 @@ def main():
     print(json.dumps(out))
 
 
+def _point_outside_subgroup(cx):
+    from oracle import curve as OC
+    rnd = random.Random(3)
+    while True:
+        x = rnd.randrange(cx.p)
+        y = OC.sqrt_mod((x * x * x + cx.G1.b) % cx.p, cx.p)
+        if y is not None and cx.G1.mul((x, y), cx.r) is not None:
+            return (x, y)
+
+
 BATCH_CASES = (("bn254", 96), ("bls12_377", 40), ("bw6_761", 40))
 
 
-def main_batch():
+def main_batch(edge=False):
     """b200_pairing_check_batch: many independent checks, one thread each; decisions known by construction (and a few
     confirmed by the oracle), agreement with the single-check entry point, throughput printed."""
     import numpy as np
@@ -129,9 +139,12 @@ def main_batch():
             a = rnd.randrange(1, 1 << 40)
             good = c % 3 != 1
             pairs = [(cx.G1.mul(cx.g1, a), cx.g2), (cx.G1.neg(cx.g1), cx.G2.mul(cx.g2, a if good else a + 1))]
-            if c % 7 == 3:
+            if edge and c % 7 == 3:
                 pairs[0], pairs[1] = (None, cx.g2), (cx.g1, None)        # infinities: the product is one
                 good = True
+            if edge and c % 11 == 5 and cname != "bn254":
+                pairs[0] = (_point_outside_subgroup(cx), cx.g2)          # reported as None, the other checks unaffected
+                good = None
             pairs_of.append(pairs)
             want.append(good)
             for P, Q in pairs:
@@ -143,6 +156,8 @@ def main_batch():
         out["checks_per_s"][cname] = round(n_checks / dt, 1)
         assert got == want, (cname, [i for i in range(n_checks) if got[i] != want[i]][:8])
         for c in (0, 1):              # the construction itself, confirmed by the oracle and by the single-check kernel
+            if want[c] is None:
+                continue
             assert pr.product_is_one(pairs_of[c]) == want[c]
             assert verifier.pairing_check(L.id, g1s[2 * c:2 * c + 2], g2s[2 * c:2 * c + 2]) == want[c]
         assert verifier.pairing_check_batch(L.id, [], [], 2) == []
@@ -151,4 +166,9 @@ def main_batch():
 
 
 if __name__ == "__main__":
-    main_batch() if "--batch" in sys.argv else main()
+    if "--batch-edge" in sys.argv:
+        main_batch(edge=True)
+    elif "--batch" in sys.argv:
+        main_batch()
+    else:
+        main()

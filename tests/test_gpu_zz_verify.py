@@ -27,12 +27,25 @@ def test_gpu_pairing_and_groth16_verify():
     print("pairing / verify wall ms:", res["pairing_ms"], res["verify_ms"])
 
 
-@pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="batch pairing kernels not yet run on hardware (GPU budget exhausted); CPU-verified template")
-def test_gpu_pairing_check_batch():
-    r = subprocess.run([sys.executable, os.path.join(HERE, "gpu_verify_worker.py"), "--batch"], capture_output=True, text=True,
-                       timeout=900)
+def _run_worker(flag, timeout):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "gpu_verify_worker.py"), flag], capture_output=True, text=True,
+                       timeout=timeout)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert res["ok"]
+    return res
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="batch pairing kernels not yet run on hardware (GPU budget exhausted); CPU-verified template")
+def test_gpu_pairing_check_batch():
+    """Generic inputs: every lane of a warp follows the same instruction stream."""
+    res = _run_worker("--batch", 900)
     print("batched pairing checks per second:", res["checks_per_s"])
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="batch pairing kernels not yet run on hardware (GPU budget exhausted); CPU-verified template")
+def test_gpu_pairing_check_batch_edge_cases():
+    """Points at infinity and G1 points outside the subgroup inside a batch (lanes leave the Miller loop early)."""
+    _run_worker("--batch-edge", 900)
